@@ -1,0 +1,268 @@
+/*
+ * wayne_b200.h -- C ABI of libwayne_b200.so: the B200 (sm_100a) replacement for
+ * the hot path of ucl-exoplanets/wayne (per-exposure detector-image synthesis).
+ *
+ * Boundary rules: extern "C", plain pointers and sizes, no torch / C++ types.
+ * Every `d_` / "device" pointer is a CUDA device pointer owned by the caller
+ * (the Python host layer allocates them as torch tensors); every `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  All entry
+ * points return WB200_OK (0) or a negative status; wb200_last_error() returns
+ * the message of the last failure on the calling thread.  Nothing throws
+ * across the boundary.  Launches are asynchronous on `stream` unless stated.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * the reference tree).
+ */
+#ifndef WAYNE_B200_H
+#define WAYNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB200_OK 0
+#define WB200_ERR_ARG -1
+#define WB200_ERR_CUDA -2
+#define WB200_ERR_NOMEM -3
+#define WB200_ERR_LOST -4      /* an electron fell outside its HBM window */
+
+/* How the electron normals are produced (a12 of the scope table). */
+#define WB200_RNG_PHILOX 0     /* native: Philox4x32-10 counter streams, fp32 Box-Muller   */
+#define WB200_RNG_RANDR 1      /* compat: glibc rand_r stream of the reference, fp64,       */
+                               /*         chunked/seeded per OpenMP thread like PSF()       */
+#define WB200_RNG_HOST 2       /* deterministic: normals supplied by the caller (A table)   */
+
+/* How expected counts become integer counts (exposure_generator.py:625-628). */
+#define WB200_COUNT_NONE 0     /* counts supplied by the caller                              */
+#define WB200_COUNT_ROUND 1    /* np.round (half to even)  -- add_stellar_noise=False         */
+#define WB200_COUNT_POISSON 2  /* Philox Poisson draw      -- add_stellar_noise=True, native */
+
+const char *wb200_last_error(void);
+int wb200_version(void);
+/* Number of CUDA devices visible, or a negative status. */
+int wb200_device_count(void);
+/* Kernels launched by this library since load (all threads); the bench's
+ * "gpu_launches" claim is read from here. */
+uint64_t wb200_launch_count(void);
+
+/* --------------------------------------------------------------------------
+ * Drop-in for the reference's only native symbol
+ *   int *PSF(int *counts,int size,double *x_pos,double *y_pos,double *psf_ratio,
+ *            double *psf_sigmal,double *psf_sigmah,int nr,int nc,int test,int threads)
+ * (wayne/pyparallel_menu.h:1-3, wayne/pyparallel_menu.c:10-113; bound by
+ * wayne/pyparallel.pyx:10-12).  Same contract: HOST pointers in (borrowed,
+ * never written), a malloc'd int[nr*nc] out that the CALLER frees, result
+ * identical to the reference for the same (test, threads) -- the rand_r stream
+ * and the per-thread chunking are reproduced on the GPU.  Returns NULL on a
+ * CUDA failure (the reference cannot fail; see wb200_last_error()).
+ * Synchronous.  Runs on the current CUDA device.
+ * -------------------------------------------------------------------------- */
+int *PSF(int *counts, int size, double *x_pos, double *y_pos, double *psf_ratio,
+         double *psf_sigmal, double *psf_sigmah, int nr, int nc, int test,
+         int threads);
+
+/* Same computation, caller-owned output, explicit status, optional
+ * caller-supplied normals (rng_mode WB200_RNG_HOST: normals = A[2*ssum] laid
+ * out as in pyparallel_menu.c:61-62) or Philox (key = test).  HOST pointers. */
+int wb200_psf_host(const int *counts, int size, const double *x_pos,
+                   const double *y_pos, const double *psf_ratio,
+                   const double *psf_sigmal, const double *psf_sigmah, int nr,
+                   int nc, int test, int threads, int rng_mode,
+                   const double *normals, int *frame_out);
+
+/* --------------------------------------------------------------------------
+ * Stage 1a: wavelength-only tables, one thread per bin.
+ * Replaces G141.set_current_wavelength_only_dependent_array (wayne/grism.py:
+ * 111-118: three np.poly1d evaluations + np.interp of the sensitivity table)
+ * and tools.bin_centers_to_widths (wayne/tools.py:106-128).
+ * d_wl [n_bins] microns.  psf_poly = ratio[4], sigmal[4], sigmah[4], highest
+ * power first (grism.py:85-90).  d_sens_wl/d_sens_val [n_sens] (microns).
+ * Outputs [n_bins] each: ratio, sigl, sigh, sens, dwl (microns).
+ * -------------------------------------------------------------------------- */
+int wb200_bin_tables(int n_bins, const double *d_wl, const double *psf_poly12,
+                     int n_sens, const double *d_sens_wl,
+                     const double *d_sens_val, double *d_ratio, double *d_sigl,
+                     double *d_sigh, double *d_sens, double *d_dwl,
+                     void *stream);
+
+/* --------------------------------------------------------------------------
+ * Stage 1b: field-dependent trace / dispersion per sub-sample, one thread per
+ * sub-sample.  Replaces wavelength_calibration_coeffs (wayne/grism.py:779-803)
+ * and _SpectrumTrace.__init__/_get_x_to_wl_poly_coeffs (grism.py:491-506,
+ * 553-602).  d_xref/d_yref [n_samples] = the sub-sample reference position
+ * (incl. jitter and scan offset).  trace_coeff9 / wl_sol9 = grism.py:756-776.
+ * d_trace [n_samples][8] = {x_ref, y_ref, m_t, c_t, m_w, c_w, m_wl, c_wl}.
+ * -------------------------------------------------------------------------- */
+#define WB200_TRACE_STRIDE 8
+int wb200_trace_table(int n_samples, const double *d_xref, const double *d_yref,
+                      const double *trace_coeff9, const double *wl_sol9,
+                      double *d_trace, void *stream);
+
+/* Parity/debug helper: x_pos,y_pos [n_samples][n_bins] on the detector for
+ * every (sub-sample, bin) = _SpectrumTrace.wl_to_x / wl_to_y (grism.py:635-669)
+ * minus sub_scale (exposure_generator.py:630-632).  The photon kernel evaluates
+ * the same device function inline. */
+int wb200_trace_positions(int n_samples, int n_bins, const double *d_trace,
+                          const double *d_wl, double sub_scale, double *d_xpos,
+                          double *d_ypos, void *stream);
+
+/* --------------------------------------------------------------------------
+ * Stage 1c + Poisson: expected electrons per (sub-sample, bin) and their
+ * integer draw.  Replaces _gen_subsample's flux->counts algebra
+ * (wayne/exposure_generator.py:344-348, 602-628; _flux_to_counts :649-687).
+ *   expected = flux[w]*(1-depth[s][w]) * sens[w] * dwl[w] * 1e4 * dur_ms[s]
+ *              * 1e-3 * scale
+ * d_depth may be NULL (no planet); depth_ld = row stride of d_depth.
+ * d_expected (nullable) [n_samples][n_bins] float64 out.
+ * d_counts  (nullable) [n_samples][n_bins] int32 out, per count_mode.
+ * d_totals  [n_samples] uint64 out: electrons per sub-sample (zeroed here).
+ * Philox key = (key0,key1); counter = (attempt, bin, sample, stream id).
+ * -------------------------------------------------------------------------- */
+int wb200_counts(int n_samples, int n_bins, const double *d_flux,
+                 const double *d_depth, int64_t depth_ld, const double *d_sens,
+                 const double *d_dwl, const double *d_dur_ms, double scale,
+                 int count_mode, uint32_t key0, uint32_t key1,
+                 double *d_expected, int32_t *d_counts, uint64_t *d_totals,
+                 void *stream);
+
+/* Exclusive prefix of counts along bins, per sub-sample (electron offsets of
+ * the compat / deterministic modes = the reference's running electron_counter,
+ * pyparallel_menu.c:86-107).  d_offsets [n_samples][n_bins] int32. */
+int wb200_count_offsets(int n_samples, int n_bins, const int32_t *d_counts,
+                        int32_t *d_offsets, void *stream);
+
+/* --------------------------------------------------------------------------
+ * Stages 2+3: throw every electron and bin it.  Replaces PSF()'s normal table
+ * and scatter loop (wayne/pyparallel_menu.c:40-64, 87-108) for ALL sub-samples
+ * of an exposure in one launch: grid = (bin chunks, sub-samples); each CTA
+ * histograms into a shared-memory tile and flushes it with integer atomics
+ * into its sub-sample's HBM window win[s][WH][WW] (origin win_ox/oy[s], frame
+ * coordinates).  Windows must be zeroed by the caller.
+ * -------------------------------------------------------------------------- */
+typedef struct wb200_photon_args {
+    int32_t n_samples;        /* sub-samples in this launch                       */
+    int32_t n_bins;           /* W                                                */
+    int32_t chunk_bins;       /* bins per CTA (multiple of 32)                    */
+    int32_t nr, nc;           /* bounds test 0<x<nr, 0<y<nc (pyparallel_menu.c:93) */
+    int32_t rng_mode;         /* WB200_RNG_*                                      */
+    int32_t threads;          /* RANDR: the reference's OpenMP thread count       */
+    int32_t win_w, win_h;     /* WW, WH                                           */
+    double sub_scale;         /* 507 - SUBARRAY/2 (exposure_generator.py:630)     */
+    uint32_t key0, key1;      /* PHILOX key                                       */
+    const int32_t *d_counts;  /* [n_samples][n_bins]                              */
+    const int32_t *d_offsets; /* [n_samples][n_bins] (RANDR / HOST), else NULL    */
+    const uint64_t *d_totals; /* [n_samples] electrons per sub-sample             */
+    const double *d_xpos;     /* explicit positions [n_samples][n_bins] or NULL   */
+    const double *d_ypos;
+    const double *d_trace;    /* [n_samples][8] when positions are NULL           */
+    const double *d_wl;       /* [n_bins] microns                                 */
+    const double *d_ratio;    /* [n_bins]                                         */
+    const double *d_sigl;
+    const double *d_sigh;
+    const int32_t *d_seeds;   /* RANDR: `test` per sub-sample                     */
+    const double *d_normals;  /* HOST: concatenated A tables                      */
+    const int64_t *d_normals_base; /* HOST: offset of sub-sample s's A table      */
+    int32_t *d_win;           /* [n_samples][win_h][win_w] int32, pre-zeroed      */
+    const int32_t *d_win_ox;  /* [n_samples] window origin x (frame coords)       */
+    const int32_t *d_win_oy;
+    uint64_t *d_lost;         /* [1] electrons inside the frame but outside their */
+                              /* window (pre-zeroed; must stay 0)                 */
+} wb200_photon_args;
+
+int wb200_throw_photons(const wb200_photon_args *args, void *stream);
+/* Same, for a batch of an exposure: sample0 = exposure-wide index of the batch's
+ * first sub-sample (Philox counters use exposure-wide indices, so the result
+ * does not depend on how an exposure is batched). */
+int wb200_throw_photons_at(const wb200_photon_args *args, int sample0, void *stream);
+
+/* --------------------------------------------------------------------------
+ * Stage 3b: flat field + accumulation into the per-read-interval planes, in
+ * sub-sample order per pixel (deterministic).  Replaces G141.get_flat_field's
+ * indices branch (wayne/grism.py:359-385), `new_pixel_array *= flat_field`
+ * (exposure_generator.py:641-645) and `pixel_array += sample_frame` (:359).
+ * d_acc [n_reads][F][F] float64, bordered layout (light-sensitive pixel (r,c)
+ * lives at (r+border, c+border)); accumulated INTO (zero it first).
+ * -------------------------------------------------------------------------- */
+typedef struct wb200_gather_args {
+    int32_t n_samples;          /* sub-samples in the window buffer            */
+    int32_t sample0;            /* global index of the first of them           */
+    int32_t n_reads;            /* R                                           */
+    int32_t L, F, border;       /* geometry                                    */
+    int32_t win_w, win_h;
+    int32_t add_flat;
+    int32_t flat_off;           /* (1014 - SUBARRAY) floor-div 2 (grism.py:361) */
+    int32_t flat_n;             /* side of the flat planes (1014)              */
+    double flat_wmin, flat_wmax;
+    const int32_t *d_read_end;  /* [R] global index of each read's last sample */
+    const int32_t *d_win;
+    const int32_t *d_win_ox;    /* indexed by local sample                     */
+    const int32_t *d_win_oy;
+    const double *d_trace;      /* indexed by local sample                     */
+    const double *d_flat[4];    /* f0..f3 [flat_n][flat_n]                     */
+    double *d_acc;
+} wb200_gather_args;
+
+int wb200_gather_flat(const wb200_gather_args *args, void *stream);
+
+/* --------------------------------------------------------------------------
+ * Stage 4: the fused per-pixel pass over all reads.  Replaces
+ * _add_read_reductions (wayne/exposure_generator.py:468-515), the cumulative
+ * read stack (:378-382), _post_exposure_reductions (:407-444) and the
+ * Exposure/WFC3_IR methods it calls (wayne/exposure.py:49-131,
+ * wayne/detector.py:151-198, 318-350).  One thread owns a pixel for the whole
+ * ramp, so every calibration plane is read once.  All planes are [F][F]
+ * float64 in the bordered layout; nullable planes switch their term off.
+ * Draw planes (compat mode) carry host-generated numpy draws; when NULL and
+ * the term is enabled the kernel draws from Philox.
+ * d_out [n_reads+1][F][F]: read 0 is the zero read.
+ * -------------------------------------------------------------------------- */
+typedef struct wb200_reads_args {
+    int32_t n_reads;            /* R = NSAMP-1                                  */
+    int32_t F, border;
+    int32_t out_f32;            /* 0: float64 output, 1: float32 output         */
+    int32_t add_noise, add_sky, add_dark, add_nonlinear, clip, add_read_noise;
+    int32_t exact_newton;       /* 1: reference's global stopping rule          */
+    int32_t n_cosmics;          /* length of the hit list                       */
+    uint32_t key0, key1;
+    double noise_mean, noise_std;   /* per second (exposure_generator.py:477-479) */
+    double sky_rate;            /* counts/s                                     */
+    double const_gain;          /* 2.35, used when d_gain == NULL               */
+    double clip_lo, clip_hi;    /* -20, 78000                                   */
+    double read_noise;          /* 14.1/2.35                                    */
+    const double *d_dt;         /* [R] read interval lengths, seconds           */
+    const double *d_acc;        /* [R][F][F] electrons per interval             */
+    const double *d_sky;        /* master sky plane                             */
+    const double *d_gain;       /* 2.35/pfl plane or NULL                       */
+    const double *d_zero;       /* zero read (initial bias) or NULL (= zeros)   */
+    const double *d_dark;       /* [R][F][F] or NULL                            */
+    const double *d_dark_err;   /* [R][F][F]                                    */
+    const double *d_nl[7];      /* 1+c1, c2, c3, c4, 2*c2, 3*c3, 4*c4           */
+    const double *d_draw_noise; /* [R][F][F] compat: N(mu*dt, sd*dt) draws      */
+    const double *d_draw_sky;   /* [R][F][F] compat: Poisson draws              */
+    const double *d_draw_dark;  /* [R][F][F] compat: N(dark, err) draws         */
+    const double *d_draw_rn;    /* [R+1][F][F] compat: standard normals         */
+    const int32_t *d_cos_head;  /* [F][F] first hit of the pixel or -1 (NULL=off) */
+    const int32_t *d_cos_next;  /* [n_cosmics]                                  */
+    const int32_t *d_cos_read;  /* [n_cosmics] read interval of the hit         */
+    const double *d_cos_energy; /* [n_cosmics]                                  */
+    int32_t *d_newton_iters;    /* [R] scratch for exact_newton (zeroed here)   */
+    void *d_out;
+} wb200_reads_args;
+
+int wb200_reads(const wb200_reads_args *args, void *stream);
+
+/* Cosmic-ray hit list -> per-pixel chains (cosmic_rays.py:70-86 scatter).
+ * d_head [F*F] is set to -1 and filled; d_next [n] out. */
+int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels,
+                        int32_t *d_head, int32_t *d_next, void *stream);
+
+/* Microbenchmarks used for the roofline denominators (profiles/): shared-memory
+ * atomic and global red rates.  Returns elapsed ms in *ms_out.  Synchronous. */
+int wb200_microbench(int which, int iters, double *ms_out, double *ops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAYNE_B200_H */

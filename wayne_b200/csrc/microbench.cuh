@@ -1,0 +1,77 @@
+// microbench.cuh -- measured denominators for the photon stage's roofline:
+// shared-memory atomic rate (conflict-free / same-address / PSF-like),
+// global red rate, Philox and Box-Muller issue rates.  Run through
+// wb200_microbench(); numbers are recorded in profiles/.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace wb {
+
+constexpr int MB_TILE = 8192; // ints of shared memory per CTA
+
+// which: 0 same address per warp, 1 conflict-free (lane -> own bank),
+//        2 PSF-like (3x3 neighbourhood per warp, pseudo-random), 3 random over the tile
+__global__ void __launch_bounds__(256) k_mb_smem_atomic(int which, int iters, int *sink)
+{
+    __shared__ int tile[MB_TILE];
+    for (int i = threadIdx.x; i < MB_TILE; i += blockDim.x)
+        tile[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t h = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        h = h * 1664525u + 1013904223u;
+        int idx;
+        if (which == 0)
+            idx = (warp * 131 + it) & (MB_TILE - 1);
+        else if (which == 1)
+            idx = ((warp * 64 + (it & 63)) * 32 + lane) & (MB_TILE - 1);
+        else if (which == 2) {
+            const int dx = (h >> 28) % 3, dy = (h >> 20) % 3;
+            idx = ((warp * 5 + dy) * 128 + ((it >> 4) & 63) + dx) & (MB_TILE - 1);
+        } else
+            idx = (h >> 12) & (MB_TILE - 1);
+        atomicAdd(&tile[idx], 1);
+    }
+    __syncthreads();
+    int acc = 0;
+    for (int i = threadIdx.x; i < MB_TILE; i += blockDim.x)
+        acc += tile[i];
+    if (acc == -1)
+        sink[0] = acc;
+}
+
+// global red.add.s32 over a 64 MB region (spread) or a 256 KB window (hot)
+__global__ void __launch_bounds__(256) k_mb_global_red(int which, int iters, int *buf, int n)
+{
+    uint32_t h = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 99u;
+    const int mask = (which == 4) ? (n - 1) : (65536 - 1);
+    for (int it = 0; it < iters; ++it) {
+        h = h * 1664525u + 1013904223u;
+        atomicAdd(&buf[(h >> 6) & mask], 1);
+    }
+}
+
+// Philox + fp32 Box-Muller pair, no memory: the ALU/SFU ceiling per electron
+__global__ void __launch_bounds__(256) k_mb_rng(int which, int iters, int *sink)
+{
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    float accf = 0.f;
+    uint32_t acci = 0;
+    for (int it = 0; it < iters; ++it) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)it, t, 7u, 2u), 0x1234u, 0x5678u);
+        if (which == 6) {
+            acci ^= r.x ^ r.y ^ r.z ^ r.w;
+        } else {
+            float a, b, c, d;
+            box_muller_f(r.x, r.y, a, b);
+            box_muller_f(r.z, r.w, c, d);
+            accf += a + b + c + d;
+        }
+    }
+    if (accf == 1.2345f || acci == 0x7fffffffu)
+        sink[0] = 1;
+}
+
+} // namespace wb

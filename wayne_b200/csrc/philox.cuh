@@ -1,0 +1,152 @@
+// philox.cuh -- counter-based random streams of the native (WB200_RNG_PHILOX)
+// mode: Philox4x32-10 (Salmon et al., SC'11; Random123 constants), uniform /
+// normal / Poisson samplers built on it.  Every draw is addressed by
+// (key, counter) only, so results do not depend on launch geometry, batching
+// or the number of GPUs.
+//
+// Counter layout used across the library: {draw index, minor id, major id,
+// stream id}; see the WB_STREAM_* ids.
+#pragma once
+#include "common.cuh"
+
+namespace wb {
+
+enum : uint32_t {
+    WB_STREAM_COUNTS = 1,  // Poisson draw of a (sub-sample, bin) cell
+    WB_STREAM_PHOTONS = 2, // Box-Muller pairs of a cell's electrons
+    WB_STREAM_NOISE = 3,   // per-read background noise normal
+    WB_STREAM_SKY = 4,     // per-read sky Poisson
+    WB_STREAM_DARK = 5,    // dark-current normal
+    WB_STREAM_READ = 6,    // read-noise normal
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// (0,1] style uniforms: (x + 0.5) * 2^-32, never 0.
+__device__ __forceinline__ float u01f(uint32_t x)
+{
+    return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+__device__ __forceinline__ double u01d(uint32_t x)
+{
+    return ((double)x + 0.5) * 2.3283064365386963e-10;
+}
+
+// fp32 Box-Muller on the SFU: lg2 + sqrt + sin + cos (4 MUFU ops per pair).
+// theta is taken in (-pi, pi] where sin.approx/cos.approx are at their stated
+// accuracy (abs err 2^-21.4).  |z| <= sqrt(2*33*ln2) = 6.77.
+constexpr float WB_ZMAX_PHILOX = 6.8f;
+__device__ __forceinline__ void box_muller_f(uint32_t a, uint32_t b, float &zx, float &zy)
+{
+    const float u1 = u01f(a);
+    const float th = fmaf((float)b, 1.4629180792671596e-09f, -3.14159265358979f); // 2pi*2^-32*b - pi
+    // -2 ln u = -2 ln2 * lg2(u)
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));
+    float s, c;
+    __sincosf(th, &s, &c);
+    zx = r * c;
+    zy = r * s;
+}
+
+// fp64 normal pair from two 32-bit words (per-pixel noise terms; accuracy over speed)
+__device__ __forceinline__ void box_muller_d(uint32_t a, uint32_t b, double &z0, double &z1)
+{
+    const double u1 = u01d(a);
+    const double u2 = u01d(b);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// A small stateful view of one Philox stream: counter.x walks, the other three
+// words address the stream.  Used by the Poisson samplers which need an
+// unbounded number of uniforms.
+struct PhiloxStream {
+    uint32_t k0, k1, cy, cz, cw, cx;
+    uint4 buf;
+    int have;
+    __device__ __forceinline__ PhiloxStream(uint32_t k0_, uint32_t k1_, uint32_t minor,
+                                            uint32_t major, uint32_t stream)
+        : k0(k0_), k1(k1_), cy(minor), cz(major), cw(stream), cx(0), have(0)
+    {
+    }
+    __device__ __forceinline__ uint32_t next()
+    {
+        if (have == 0) {
+            buf = philox4x32_10(make_uint4(cx++, cy, cz, cw), k0, k1);
+            have = 4;
+        }
+        uint32_t v = buf.x;
+        buf.x = buf.y;
+        buf.y = buf.z;
+        buf.z = buf.w;
+        --have;
+        return v;
+    }
+    __device__ __forceinline__ double uniform() { return u01d(next()); }
+};
+
+// Exact Poisson sampler (distribution-exact, not a normal approximation):
+//  lam < 10 : multiplication method (Knuth)
+//  lam >= 10: PTRS transformed rejection (Hoermann 1993, "The transformed
+//             rejection method for generating Poisson random variables") --
+//             the same two algorithms numpy's legacy poisson uses, so the
+//             distribution matches np.random.poisson (exposure_generator.py:626,495).
+__device__ inline long long poisson_draw(PhiloxStream &g, double lam)
+{
+    if (!(lam > 0.0))
+        return 0;
+    if (lam < 10.0) {
+        const double enlam = exp(-lam);
+        long long k = 0;
+        double prod = g.uniform();
+        while (prod > enlam) {
+            prod *= g.uniform();
+            ++k;
+        }
+        return k;
+    }
+    const double slam = sqrt(lam);
+    const double loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const double U = g.uniform() - 0.5;
+        const double V = g.uniform();
+        const double us = 0.5 - fabs(U);
+        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr)
+            return (long long)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us))
+            continue;
+        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <=
+            (-lam + kf * loglam - lgamma(kf + 1.0)))
+            return (long long)kf;
+    }
+}
+
+} // namespace wb

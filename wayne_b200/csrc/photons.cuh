@@ -1,0 +1,338 @@
+// photons.cuh -- stages 2+3: throw every electron of an exposure and bin it.
+//
+// Replaces the reference's PSF() (wayne/pyparallel_menu.c:10-113): its
+// 16 B/electron normal table, and its SERIAL scatter loop, for all sub-samples
+// of an exposure in one launch.
+//
+// Mapping to B200
+//   grid  = (bin chunks, sub-samples): thousands of CTAs over 148 SMs.
+//   CTA   = 256 threads, a TH x TW int32 histogram tile in shared memory placed
+//           on the footprint of its bin chunk (trace segment +- ~4 sigma_h).
+//   warp  = takes 32 consecutive bins; a warp-level prefix sum of their work
+//           units turns the ragged "counts[bin] electrons per bin" loop into a
+//           dense stream of units, one per lane (load balance is exact
+//           whatever the counts are); the unit -> bin lookup is a 5-step
+//           shuffle binary search, bin parameters are fetched by shuffle.
+//   unit  = PHILOX: one Philox4x32-10 call = 2 electrons of one bin
+//           RANDR / HOST: one electron (fp64, bit-compatible with the reference)
+//   bin   = shared-memory atomicAdd into the tile; electrons that leave the
+//           tile but not the frame go straight to the HBM window with a global
+//           reduction (rare: |z| > ~4).  At the end the tile is flushed to the
+//           sub-sample's HBM window with integer `red.global.add` -- integer
+//           adds commute, so the histogram is deterministic.
+//   HBM traffic per electron is ~0 by construction; the stage is bound by
+//   shared-memory atomics and SFU/ALU work (roofline).
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+#include "stage1.cuh"
+
+namespace wb {
+
+// ---- glibc rand_r restated for the compat stream ---------------------------
+// state <- state*1103515245 + 12345 (mod 2^32); one rand_r() = 3 steps.
+// LCG jump tables: after 2^k steps, s -> A[k]*s + C[k].
+__constant__ uint32_t c_lcg_A[32];
+__constant__ uint32_t c_lcg_C[32];
+
+__device__ __forceinline__ uint32_t lcg_skip(uint32_t s, uint32_t n)
+{
+    while (n) {
+        const int k = __ffs(n) - 1;
+        s = c_lcg_A[k] * s + c_lcg_C[k];
+        n &= n - 1;
+    }
+    return s;
+}
+
+__device__ __forceinline__ int rand_r_dev(uint32_t &s)
+{
+    s = s * 1103515245u + 12345u;
+    uint32_t out = (s >> 16) & 0x7ffu;
+    s = s * 1103515245u + 12345u;
+    out = (out << 10) ^ ((s >> 16) & 0x3ffu);
+    s = s * 1103515245u + 12345u;
+    out = (out << 10) ^ ((s >> 16) & 0x3ffu);
+    return (int)out;
+}
+
+// first electron of OpenMP thread t of T over ssum electrons (pyparallel_menu.c:47-49)
+__device__ __forceinline__ long long chunk_begin(int t, int T, long long ssum)
+{
+    return (t >= T) ? ssum : (t * ssum) / T;
+}
+
+// The reference's normal pair of electron e of a sub-sample (pyparallel_menu.c:52-62).
+__device__ inline void randr_normals(long long e, long long ssum, int T, int test, double &zx,
+                                     double &zy)
+{
+    int t = (int)((e * T) / ssum);
+    if (t >= T)
+        t = T - 1;
+    while (t + 1 < T && chunk_begin(t + 1, T, ssum) <= e)
+        ++t;
+    while (t > 0 && chunk_begin(t, T, ssum) > e)
+        --t;
+    const long long first = chunk_begin(t, T, ssum);
+    uint32_t st = (uint32_t)(25234 + 17 * t + test);
+    st = lcg_skip(st, (uint32_t)(6ull * (unsigned long long)(e - first)));
+    const int r1 = rand_r_dev(st);
+    const int r2 = rand_r_dev(st);
+    const double theta = (2. * 3.14159265358979323846) * (double)r1 / 2147483647.0;
+    const double R = sqrt(-2. * log((double)r2 / 2147483647.0));
+    zx = R * cos(theta);
+    zy = R * sin(theta);
+}
+
+struct PhotonParams {
+    wb200_photon_args a;
+    int sample0; // global index of the launch's first sub-sample (Philox counters)
+};
+
+template <int TW, int TH>
+struct Tile {
+    int x0, y0;         // frame coordinates of tile cell (0,0)
+    int lox, hix;       // accepted tile-relative x range [lox, hix)  (frame: 0 < x < nr)
+    int loy, hiy;
+};
+
+// Frame-accepted electron at absolute pixel (xa, ya) that missed the tile.
+__device__ __forceinline__ void to_window(const wb200_photon_args &a, int s_local, int ox, int oy,
+                                          int xa, int ya)
+{
+    const int wx = xa - ox, wy = ya - oy;
+    if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
+        atomicAdd(&a.d_win[((size_t)s_local * a.win_h + wy) * a.win_w + wx], 1);
+    else
+        atomicAdd((unsigned long long *)a.d_lost, 1ull);
+}
+
+template <int MODE, int TW, int TH>
+__global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
+{
+    const wb200_photon_args &a = p.a;
+    extern __shared__ int tile[]; // TH*TW
+    __shared__ float s_red[4][8];
+    __shared__ int s_org[2];
+
+    const int s_local = blockIdx.y;
+    const int s_glob = p.sample0 + s_local;
+    const int W = a.n_bins;
+    const int w0 = blockIdx.x * a.chunk_bins;
+    const int w1 = min(W, w0 + a.chunk_bins);
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+
+    const long long ssum = a.d_totals ? (long long)a.d_totals[s_local] : 0;
+    if (ssum == 0 && a.d_totals)
+        return; // nothing to throw in this sub-sample (uniform over the CTA)
+
+    TraceCoef tc;
+    if (!a.d_xpos)
+        tc = load_trace(a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE);
+    const size_t row = (size_t)s_local * W;
+
+    auto bin_xy = [&](int w, double &x, double &y) {
+        if (a.d_xpos) {
+            x = a.d_xpos[row + w];
+            y = a.d_ypos[row + w];
+        } else {
+            trace_xy(tc, a.d_wl[w], a.sub_scale, x, y);
+        }
+    };
+
+    // ---- place the tile on the chunk's footprint -------------------------
+    float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+    for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+        if (a.d_counts[row + w] <= 0)
+            continue;
+        double x, y;
+        bin_xy(w, x, y);
+        // NaN / inf positions never bin; keep them out of the bounding box
+        if (!(fabs(x) < 1e9) || !(fabs(y) < 1e9))
+            continue;
+        xmin = fminf(xmin, (float)x);
+        xmax = fmaxf(xmax, (float)x);
+        ymin = fminf(ymin, (float)y);
+        ymax = fmaxf(ymax, (float)y);
+    }
+    xmin = warp_min(xmin);
+    xmax = warp_max(xmax);
+    ymin = warp_min(ymin);
+    ymax = warp_max(ymax);
+    if (lane == 0) {
+        s_red[0][warp] = xmin;
+        s_red[1][warp] = xmax;
+        s_red[2][warp] = ymin;
+        s_red[3][warp] = ymax;
+    }
+    for (int i = threadIdx.x; i < TW * TH; i += blockDim.x)
+        tile[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < nwarps; ++i) {
+            xmin = fminf(xmin, s_red[0][i]);
+            xmax = fmaxf(xmax, s_red[1][i]);
+            ymin = fminf(ymin, s_red[2][i]);
+            ymax = fmaxf(ymax, s_red[3][i]);
+        }
+        int ox = 0, oy = 0;
+        if (xmin <= xmax) {
+            ox = (int)floorf(0.5f * (xmin + xmax)) - TW / 2;
+            oy = (int)floorf(0.5f * (ymin + ymax)) - TH / 2;
+        }
+        s_org[0] = ox;
+        s_org[1] = oy;
+    }
+    __syncthreads();
+    Tile<TW, TH> T;
+    T.x0 = s_org[0];
+    T.y0 = s_org[1];
+    T.lox = max(0, 1 - T.x0);
+    T.hix = min(TW, a.nr - T.x0);
+    T.loy = max(0, 1 - T.y0);
+    T.hiy = min(TH, a.nc - T.y0);
+    const int wox = a.d_win_ox[s_local], woy = a.d_win_oy[s_local];
+
+    // ---- the electrons ------------------------------------------------------
+    const int ngroups = (w1 - w0 + 31) >> 5;
+    for (int g = warp; g < ngroups; g += nwarps) {
+        const int wb = w0 + (g << 5);
+        const int w = wb + lane;
+        int cnt = 0, nh = 0, off = 0;
+        double bx = 0, by = 0, bsl = 0, bsh = 0;
+        if (w < w1) {
+            cnt = a.d_counts[row + w];
+            if (cnt > 0) {
+                bin_xy(w, bx, by);
+                bsl = a.d_sigl[w];
+                bsh = a.d_sigh[w];
+                // N = counts*psf_ratio truncated: the first N electrons of the
+                // bin take the wide Gaussian (pyparallel_menu.c:89-98)
+                nh = __double2int_rz((double)cnt * a.d_ratio[w]);
+                if (MODE != WB200_RNG_PHILOX)
+                    off = a.d_offsets[row + w];
+            } else {
+                cnt = 0;
+            }
+        }
+        const int units = (MODE == WB200_RNG_PHILOX) ? ((cnt + 1) >> 1) : cnt;
+        const int incl = warp_incl_scan(units);
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int excl = incl - units;
+
+        if (MODE == WB200_RNG_PHILOX) {
+            // tile-relative fp32 copies of the bin parameters
+            const float fx = (float)(bx - (double)T.x0);
+            const float fy = (float)(by - (double)T.y0);
+            const float fsl = (float)bsl, fsh = (float)bsh;
+            for (int base = 0; base < total; base += 32) {
+                const int q = base + lane;
+                int b = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, b + step - 1);
+                    if (v <= q)
+                        b += step;
+                }
+                const int ucnt = __shfl_sync(FULL, cnt, b);
+                const int unh = __shfl_sync(FULL, nh, b);
+                const int uex = __shfl_sync(FULL, excl, b);
+                const float ux = __shfl_sync(FULL, fx, b);
+                const float uy = __shfl_sync(FULL, fy, b);
+                const float usl = __shfl_sync(FULL, fsl, b);
+                const float ush = __shfl_sync(FULL, fsh, b);
+                if (q >= total)
+                    continue;
+                const int j = q - uex;
+                const uint4 r = philox4x32_10(
+                    make_uint4((uint32_t)j, (uint32_t)(wb + b), (uint32_t)s_glob, WB_STREAM_PHOTONS),
+                    a.key0, a.key1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = 2 * j + h;
+                    if (k >= ucnt)
+                        break;
+                    float zx, zy;
+                    box_muller_f(h ? r.z : r.x, h ? r.w : r.y, zx, zy);
+                    const float sg = (k < unh) ? ush : usl;
+                    // floor on tile-relative coordinates == the reference's (int)
+                    // truncation on frame coordinates for every accepted electron
+                    // (x in (-1,1) is rejected either way by the strict 0 < x test)
+                    const int ix = __float2int_rd(fmaf(zx, sg, ux));
+                    const int iy = __float2int_rd(fmaf(zy, sg, uy));
+                    if (ix >= T.lox && ix < T.hix && iy >= T.loy && iy < T.hiy) {
+                        atomicAdd(&tile[iy * TW + ix], 1);
+                    } else {
+                        const int xa = ix + T.x0, ya = iy + T.y0;
+                        if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc)
+                            to_window(a, s_local, wox, woy, xa, ya);
+                    }
+                }
+            }
+        } else {
+            const double *An = nullptr;
+            if (MODE == WB200_RNG_HOST)
+                An = a.d_normals + a.d_normals_base[s_local];
+            const int test = (MODE == WB200_RNG_RANDR) ? a.d_seeds[s_local] : 0;
+            for (int base = 0; base < total; base += 32) {
+                const int q = base + lane;
+                int b = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, b + step - 1);
+                    if (v <= q)
+                        b += step;
+                }
+                const int unh = __shfl_sync(FULL, nh, b);
+                const int uex = __shfl_sync(FULL, excl, b);
+                const int uoff = __shfl_sync(FULL, off, b);
+                const double ux = shfl_d(bx, b);
+                const double uy = shfl_d(by, b);
+                const double usl = shfl_d(bsl, b);
+                const double ush = shfl_d(bsh, b);
+                if (q >= total)
+                    continue;
+                const int j = q - uex;
+                const long long e = (long long)uoff + j;
+                double zx, zy;
+                if (MODE == WB200_RNG_HOST) {
+                    zx = An[e];
+                    zy = An[e + ssum];
+                } else {
+                    randr_normals(e, ssum, a.threads, test, zx, zy);
+                }
+                const double sg = (j < unh) ? ush : usl;
+                // xpos = (int)(A*sigma + x_pos): separate multiply and add, C
+                // truncation (pyparallel_menu.c:91-92); out-of-range values
+                // saturate and fail the bounds test like the reference's INT_MIN
+                const int xa = __double2int_rz(__dadd_rn(__dmul_rn(zx, sg), ux));
+                const int ya = __double2int_rz(__dadd_rn(__dmul_rn(zy, sg), uy));
+                if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
+                    const int ix = xa - T.x0, iy = ya - T.y0;
+                    if ((unsigned)ix < (unsigned)TW && (unsigned)iy < (unsigned)TH)
+                        atomicAdd(&tile[iy * TW + ix], 1);
+                    else
+                        to_window(a, s_local, wox, woy, xa, ya);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- flush the tile into the sub-sample's HBM window ----------------------
+    for (int i = threadIdx.x; i < TW * TH; i += blockDim.x) {
+        const int v = tile[i];
+        if (v) {
+            const int iy = i / TW, ix = i - iy * TW;
+            const int wx = ix + T.x0 - wox, wy = iy + T.y0 - woy;
+            if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
+                atomicAdd(&a.d_win[((size_t)s_local * a.win_h + wy) * a.win_w + wx], v);
+            else
+                atomicAdd((unsigned long long *)a.d_lost, (unsigned long long)v);
+        }
+    }
+}
+
+} // namespace wb

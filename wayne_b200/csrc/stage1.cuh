@@ -1,0 +1,250 @@
+// stage1.cuh -- trace / dispersion / sensitivity / expected counts (fp64).
+//
+// Everything here is tiny next to the photon stage, so the kernels are written
+// for EXACTNESS: each expression keeps the operation order of the numpy
+// expression it replaces and the library is built with -fmad=false, so no
+// a*b+c is fused; the parity tests then see differences of at most a few ulp
+// (gate: 1e-6 relative).
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace wb {
+
+// np.poly1d / np.polyval Horner form: y = y*x + p[i], starting from 0.
+__device__ __forceinline__ double polyval4(const double *p, double x)
+{
+    double y = p[0]; // 0*x + p0
+    y = y * x + p[1];
+    y = y * x + p[2];
+    y = y * x + p[3];
+    return y;
+}
+
+// np.interp (end-clamped linear interpolation, numpy/_core/src/multiarray/
+// compiled_base.c arr_interp): binary search for xp[j] <= x < xp[j+1].
+__device__ inline double interp1(double x, const double *xp, const double *fp, int n)
+{
+    if (x > xp[n - 1])
+        return fp[n - 1];
+    if (x < xp[0])
+        return fp[0];
+    int lo = 0, hi = n; // invariant xp[lo] <= x
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= xp[mid])
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const int j = lo;
+    if (j == n - 1 || xp[j] == x)
+        return fp[j];
+    const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    double r = slope * (x - xp[j]) + fp[j];
+    if (isnan(r)) {
+        r = slope * (x - xp[j + 1]) + fp[j + 1];
+        if (isnan(r) && fp[j] == fp[j + 1])
+            r = fp[j];
+    }
+    return r;
+}
+
+// grism.py:111-118 (+ tools.py:106-128): one thread per wavelength bin.
+__global__ void k_bin_tables(int W, const double *__restrict__ wl, const double *poly12, int ns,
+                             const double *__restrict__ sens_wl,
+                             const double *__restrict__ sens_val, double *ratio, double *sigl,
+                             double *sigh, double *sens, double *dwl)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W)
+        return;
+    const double x = wl[w];
+    ratio[w] = polyval4(poly12 + 0, x);
+    sigl[w] = polyval4(poly12 + 4, x);
+    sigh[w] = polyval4(poly12 + 8, x);
+    sens[w] = interp1(x, sens_wl, sens_val, ns);
+    // bin_centers_to_widths: half-gap to the previous centre (first bin reuses
+    // the second's) plus half-gap to the next centre (last bin reuses its own).
+    auto half_gap = [&](int i) {
+        const int k = (i == 0) ? 1 : i;
+        return (wl[k] - wl[k - 1]) / 2.;
+    };
+    const double g0 = half_gap(w);
+    const double g1 = (w == W - 1) ? half_gap(W - 1) : half_gap(w + 1);
+    dwl[w] = g0 + g1;
+}
+
+struct TraceCoef {
+    double x_ref, y_ref, m_t, c_t, m_w, c_w, m_wl, c_wl;
+};
+
+// grism.py:779-803 then :591-602 for one reference position.
+__device__ __forceinline__ TraceCoef make_trace(double x, double y, const double *a,
+                                                const double *b)
+{
+    TraceCoef t;
+    t.x_ref = x;
+    t.y_ref = y;
+    t.m_t = a[3] + a[4] * x + a[5] * y + a[6] * (x * x) + a[7] * x * y + a[8] * (y * y);
+    t.c_t = a[0] + a[1] * x + a[2] * y;
+    t.m_w = b[3] + b[4] * x + b[5] * y + b[6] * (x * x) + b[7] * x * y + b[8] * (y * y);
+    t.c_w = (b[0] + b[1] * x) + b[2] * y;
+    // two probe points at x_ref+10 / +20 on the trace -> linear lambda(x)
+    const double X0 = x + 10, X1 = x + 20;
+    const double Y0 = t.m_t * (X0 - x) + t.c_t + y;
+    const double Y1 = t.m_t * (X1 - x) + t.c_t + y;
+    const double d0 = sqrt((Y0 - y) * (Y0 - y) + (X0 - x) * (X0 - x));
+    const double d1 = sqrt((Y1 - y) * (Y1 - y) + (X1 - x) * (X1 - x));
+    const double l0 = (t.m_w * d0 + t.c_w) * 1e-4; // angstrom -> micron
+    const double l1 = (t.m_w * d1 + t.c_w) * 1e-4;
+    t.m_wl = (l1 - l0) / (X1 - X0);
+    t.c_wl = l0 - t.m_wl * X0;
+    return t;
+}
+
+// _SpectrumTrace.wl_to_x / wl_to_y (grism.py:635-669) minus the sub-array
+// shift (exposure_generator.py:630-632).
+__device__ __forceinline__ void trace_xy(const TraceCoef &t, double wl, double sub_scale,
+                                         double &x, double &y)
+{
+    const double xp = (wl - t.c_wl) / t.m_wl;
+    const double yp = t.m_t * (xp - t.x_ref) + t.c_t + t.y_ref;
+    x = xp - sub_scale;
+    y = yp - sub_scale;
+}
+
+__device__ __forceinline__ TraceCoef load_trace(const double *tr)
+{
+    TraceCoef t;
+    t.x_ref = tr[0];
+    t.y_ref = tr[1];
+    t.m_t = tr[2];
+    t.c_t = tr[3];
+    t.m_w = tr[4];
+    t.c_w = tr[5];
+    t.m_wl = tr[6];
+    t.c_wl = tr[7];
+    return t;
+}
+
+struct Coef18 {
+    double a[9], b[9];
+};
+
+__global__ void k_trace_table(int N, const double *__restrict__ xr, const double *__restrict__ yr,
+                              Coef18 c, double *trace)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N)
+        return;
+    const TraceCoef t = make_trace(xr[s], yr[s], c.a, c.b);
+    double *o = trace + (size_t)s * WB200_TRACE_STRIDE;
+    o[0] = t.x_ref;
+    o[1] = t.y_ref;
+    o[2] = t.m_t;
+    o[3] = t.c_t;
+    o[4] = t.m_w;
+    o[5] = t.c_w;
+    o[6] = t.m_wl;
+    o[7] = t.c_wl;
+}
+
+__global__ void k_trace_positions(int N, int W, const double *__restrict__ trace,
+                                  const double *__restrict__ wl, double sub_scale, double *xpos,
+                                  double *ypos)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (w >= W || s >= N)
+        return;
+    const TraceCoef t = load_trace(trace + (size_t)s * WB200_TRACE_STRIDE);
+    double x, y;
+    trace_xy(t, wl[w], sub_scale, x, y);
+    xpos[(size_t)s * W + w] = x;
+    ypos[(size_t)s * W + w] = y;
+}
+
+// exposure_generator.py:344-348 and :602-628.  grid = (ceil(W/256), N).
+__global__ void __launch_bounds__(256)
+k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict__ depth,
+         long long depth_ld, const double *__restrict__ sens, const double *__restrict__ dwl,
+         const double *__restrict__ dur_ms, double scale, int mode, uint32_t k0, uint32_t k1,
+         double *expected, int *counts, unsigned long long *totals)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    long long c = 0;
+    if (w < W) {
+        double f = flux[w];
+        if (depth)
+            f = f * (1. - depth[(size_t)s * depth_ld + w]);
+        double e = f * sens[w];  // ph / s / angstrom
+        e = e * dwl[w];          // (ph/s/A) * micron
+        e = e * 1e4;             // micron -> angstrom : ph / s
+        e = e * dur_ms[s];       // ph/s * ms
+        e = e * 1e-3;            // ms -> s : photons
+        e = e * scale;           // visit trend (exposure_generator.py:620-621)
+        if (expected)
+            expected[(size_t)s * W + w] = e;
+        if (mode == WB200_COUNT_ROUND) {
+            c = (long long)rint(e);
+        } else if (mode == WB200_COUNT_POISSON) {
+            PhiloxStream g(k0, k1, (uint32_t)w, (uint32_t)s, WB_STREAM_COUNTS);
+            c = poisson_draw(g, e);
+        } else if (counts) {
+            c = counts[(size_t)s * W + w];
+        }
+        if (c < 0)
+            c = 0;
+        if (c > 2147483647LL)
+            c = 2147483647LL; // the reference's counters are 32-bit (pyparallel_menu.c:12)
+        if (mode != WB200_COUNT_NONE && counts)
+            counts[(size_t)s * W + w] = (int)c;
+    }
+    unsigned long long v = warp_sum_u64((unsigned long long)c);
+    __shared__ unsigned long long part[8];
+    if (lane_id() == 0)
+        part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i)
+            t += part[i];
+        if (t)
+            atomicAdd(&totals[s], t);
+    }
+}
+
+// Exclusive prefix of counts along bins; one CTA (256 threads) per sub-sample.
+__global__ void __launch_bounds__(256)
+k_count_offsets(int W, const int *__restrict__ counts, int *offsets)
+{
+    const int s = blockIdx.x;
+    const int *c = counts + (size_t)s * W;
+    int *o = offsets + (size_t)s * W;
+    __shared__ int wsum[8];
+    __shared__ int carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    for (int base = 0; base < W; base += 256) {
+        const int w = base + threadIdx.x;
+        const int v = (w < W) ? c[w] : 0;
+        const int inc = warp_incl_scan(v);
+        if (lane_id() == 31)
+            wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int pre = carry;
+        for (int i = 0; i < (int)(threadIdx.x >> 5); ++i)
+            pre += wsum[i];
+        if (w < W)
+            o[w] = pre + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 255)
+            carry = pre + inc;
+        __syncthreads();
+    }
+}
+
+} // namespace wb

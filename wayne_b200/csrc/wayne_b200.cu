@@ -1,0 +1,448 @@
+// wayne_b200.cu -- the C ABI of libwayne_b200.so (see include/wayne_b200.h).
+// One translation unit: kernels live in the .cuh files next to this one.
+//
+// Build (see wayne_b200/build.py):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//        -fmad=false -Xcompiler -fPIC -shared -o libwayne_b200.so wayne_b200.cu
+// -fmad=false: the fp64 paths must reproduce numpy / C expressions that are
+// never fused on the reference's x86-64 build; the fp32 fast path asks for its
+// FMAs explicitly (fmaf).
+#include <stdlib.h>
+#include <vector>
+
+#include "common.cuh"
+#include "gather.cuh"
+#include "microbench.cuh"
+#include "philox.cuh"
+#include "photons.cuh"
+#include "reads.cuh"
+#include "stage1.cuh"
+
+namespace wb {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+static bool g_lcg_ready[64] = {};
+
+// jump tables of the rand_r LCG, uploaded once per device
+static int ensure_lcg_tables()
+{
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && g_lcg_ready[dev])
+        return WB200_OK;
+    uint32_t A[32], C[32];
+    uint32_t a = 1103515245u, c = 12345u;
+    for (int k = 0; k < 32; ++k) {
+        A[k] = a;
+        C[k] = c;
+        c = a * c + c; // two applications: a*(a*s+c)+c
+        a = a * a;
+    }
+    WB_CUDA(cudaMemcpyToSymbol(c_lcg_A, A, sizeof(A)));
+    WB_CUDA(cudaMemcpyToSymbol(c_lcg_C, C, sizeof(C)));
+    if (dev >= 0 && dev < 64)
+        g_lcg_ready[dev] = true;
+    return WB200_OK;
+}
+
+constexpr int TILE_W = 128, TILE_H = 64;
+
+template <int MODE>
+static int launch_throw(const PhotonParams &p, cudaStream_t st)
+{
+    const wb200_photon_args &a = p.a;
+    const int chunks = (a.n_bins + a.chunk_bins - 1) / a.chunk_bins;
+    dim3 grid(chunks, a.n_samples);
+    const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int);
+    k_throw<MODE, TILE_W, TILE_H><<<grid, 256, smem, st>>>(p);
+    WB_LAUNCHED("k_throw");
+    return WB200_OK;
+}
+
+static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st)
+{
+    WB_REQUIRE(a != nullptr, "null args");
+    WB_REQUIRE(a->n_samples >= 0 && a->n_bins > 0, "bad sizes");
+    WB_REQUIRE(a->chunk_bins > 0 && (a->chunk_bins % 32) == 0, "chunk_bins must be a multiple of 32");
+    WB_REQUIRE(a->d_counts && a->d_win && a->d_win_ox && a->d_win_oy && a->d_lost, "null buffer");
+    WB_REQUIRE(a->d_ratio && a->d_sigl && a->d_sigh, "null psf tables");
+    WB_REQUIRE((a->d_xpos && a->d_ypos) || (a->d_trace && a->d_wl), "no positions");
+    WB_REQUIRE(a->n_samples <= 65535, "at most 65535 sub-samples per launch");
+    if (a->n_samples == 0)
+        return WB200_OK;
+    PhotonParams p;
+    p.a = *a;
+    p.sample0 = sample0;
+    switch (a->rng_mode) {
+    case WB200_RNG_PHILOX:
+        return launch_throw<WB200_RNG_PHILOX>(p, st);
+    case WB200_RNG_RANDR: {
+        WB_REQUIRE(a->d_offsets && a->d_totals && a->d_seeds && a->threads >= 1, "RANDR inputs");
+        int rc = ensure_lcg_tables();
+        if (rc)
+            return rc;
+        return launch_throw<WB200_RNG_RANDR>(p, st);
+    }
+    case WB200_RNG_HOST:
+        WB_REQUIRE(a->d_offsets && a->d_totals && a->d_normals && a->d_normals_base, "HOST inputs");
+        return launch_throw<WB200_RNG_HOST>(p, st);
+    default:
+        return fail(WB200_ERR_ARG, "unknown rng_mode%s%s");
+    }
+}
+} // namespace wb
+
+using namespace wb;
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf()
+    {
+        if (p)
+            cudaFree(p);
+    }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+    template <typename T>
+    T *as() { return (T *)p; }
+};
+} // namespace
+
+extern "C" {
+
+const char *wb200_last_error(void) { return g_err; }
+int wb200_version(void) { return 100; }
+uint64_t wb200_launch_count(void) { return g_launches.load(); }
+
+int wb200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail(WB200_ERR_CUDA, "cudaGetDeviceCount: %s%s", cudaGetErrorString(e));
+        return WB200_ERR_CUDA;
+    }
+    return n;
+}
+
+int wb200_bin_tables(int n_bins, const double *d_wl, const double *psf_poly12, int n_sens,
+                     const double *d_sens_wl, const double *d_sens_val, double *d_ratio,
+                     double *d_sigl, double *d_sigh, double *d_sens, double *d_dwl, void *stream)
+{
+    WB_REQUIRE(n_bins >= 2 && n_sens >= 1, "need >= 2 bins and a sensitivity table");
+    WB_REQUIRE(d_wl && psf_poly12 && d_sens_wl && d_sens_val, "null input");
+    WB_REQUIRE(d_ratio && d_sigl && d_sigh && d_sens && d_dwl, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the 12 polynomial coefficients are a HOST array: stage them in a small
+    // device buffer that lives for the duration of the (stream-ordered) launch
+    double *d_poly = nullptr;
+    WB_CUDA(cudaMallocAsync(&d_poly, 12 * sizeof(double), st));
+    WB_CUDA(cudaMemcpyAsync(d_poly, psf_poly12, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_bin_tables<<<(n_bins + 127) / 128, 128, 0, st>>>(n_bins, d_wl, d_poly, n_sens, d_sens_wl,
+                                                       d_sens_val, d_ratio, d_sigl, d_sigh, d_sens,
+                                                       d_dwl);
+    WB_LAUNCHED("k_bin_tables");
+    WB_CUDA(cudaFreeAsync(d_poly, st));
+    return WB200_OK;
+}
+
+int wb200_trace_table(int n_samples, const double *d_xref, const double *d_yref,
+                      const double *trace_coeff9, const double *wl_sol9, double *d_trace,
+                      void *stream)
+{
+    WB_REQUIRE(n_samples >= 0 && d_xref && d_yref && trace_coeff9 && wl_sol9 && d_trace, "bad args");
+    if (n_samples == 0)
+        return WB200_OK;
+    Coef18 c;
+    memcpy(c.a, trace_coeff9, sizeof(c.a));
+    memcpy(c.b, wl_sol9, sizeof(c.b));
+    k_trace_table<<<(n_samples + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_samples, d_xref,
+                                                                             d_yref, c, d_trace);
+    WB_LAUNCHED("k_trace_table");
+    return WB200_OK;
+}
+
+int wb200_trace_positions(int n_samples, int n_bins, const double *d_trace, const double *d_wl,
+                          double sub_scale, double *d_xpos, double *d_ypos, void *stream)
+{
+    WB_REQUIRE(n_samples > 0 && n_samples <= 65535 && n_bins > 0, "bad sizes");
+    WB_REQUIRE(d_trace && d_wl && d_xpos && d_ypos, "null buffer");
+    dim3 grid((n_bins + 127) / 128, n_samples);
+    k_trace_positions<<<grid, 128, 0, (cudaStream_t)stream>>>(n_samples, n_bins, d_trace, d_wl,
+                                                              sub_scale, d_xpos, d_ypos);
+    WB_LAUNCHED("k_trace_positions");
+    return WB200_OK;
+}
+
+int wb200_counts(int n_samples, int n_bins, const double *d_flux, const double *d_depth,
+                 int64_t depth_ld, const double *d_sens, const double *d_dwl,
+                 const double *d_dur_ms, double scale, int count_mode, uint32_t key0,
+                 uint32_t key1, double *d_expected, int32_t *d_counts, uint64_t *d_totals,
+                 void *stream)
+{
+    WB_REQUIRE(n_samples > 0 && n_samples <= 65535 && n_bins > 0, "bad sizes");
+    WB_REQUIRE(d_flux && d_sens && d_dwl && d_dur_ms && d_totals, "null buffer");
+    WB_REQUIRE(count_mode >= 0 && count_mode <= 2, "bad count_mode");
+    WB_REQUIRE(count_mode == WB200_COUNT_NONE || d_counts, "counts output needed");
+    cudaStream_t st = (cudaStream_t)stream;
+    WB_CUDA(cudaMemsetAsync(d_totals, 0, sizeof(uint64_t) * n_samples, st));
+    dim3 grid((n_bins + 255) / 256, n_samples);
+    k_counts<<<grid, 256, 0, st>>>(n_samples, n_bins, d_flux, d_depth, (long long)depth_ld, d_sens,
+                                   d_dwl, d_dur_ms, scale, count_mode, key0, key1, d_expected,
+                                   d_counts, (unsigned long long *)d_totals);
+    WB_LAUNCHED("k_counts");
+    return WB200_OK;
+}
+
+int wb200_count_offsets(int n_samples, int n_bins, const int32_t *d_counts, int32_t *d_offsets,
+                        void *stream)
+{
+    WB_REQUIRE(n_samples > 0 && n_bins > 0 && d_counts && d_offsets, "bad args");
+    k_count_offsets<<<n_samples, 256, 0, (cudaStream_t)stream>>>(n_bins, d_counts, d_offsets);
+    WB_LAUNCHED("k_count_offsets");
+    return WB200_OK;
+}
+
+int wb200_throw_photons(const wb200_photon_args *args, void *stream)
+{
+    return throw_photons(args, 0, (cudaStream_t)stream);
+}
+
+// Batches of an exposure carry the global index of their first sub-sample so
+// Philox counters do not depend on the batching.
+int wb200_throw_photons_at(const wb200_photon_args *args, int sample0, void *stream)
+{
+    return throw_photons(args, sample0, (cudaStream_t)stream);
+}
+
+int wb200_gather_flat(const wb200_gather_args *a, void *stream)
+{
+    WB_REQUIRE(a != nullptr, "null args");
+    WB_REQUIRE(a->n_reads > 0 && a->n_reads <= 65535 && a->L > 0 && a->F >= a->L, "bad geometry");
+    WB_REQUIRE(a->d_read_end && a->d_win && a->d_win_ox && a->d_win_oy && a->d_trace && a->d_acc,
+               "null buffer");
+    WB_REQUIRE(!a->add_flat || (a->d_flat[0] && a->d_flat[1] && a->d_flat[2] && a->d_flat[3]),
+               "flat planes missing");
+    if (a->n_samples == 0)
+        return WB200_OK;
+    dim3 grid((a->L + GX - 1) / GX, (a->L + GY - 1) / GY, a->n_reads);
+    dim3 block(GX, GY);
+    k_gather<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+    WB_LAUNCHED("k_gather");
+    return WB200_OK;
+}
+
+int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels, int32_t *d_head,
+                        int32_t *d_next, void *stream)
+{
+    WB_REQUIRE(n_hits >= 0 && n_pixels > 0 && d_head, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    WB_CUDA(cudaMemsetAsync(d_head, 0xff, sizeof(int32_t) * (size_t)n_pixels, st));
+    if (n_hits == 0)
+        return WB200_OK;
+    WB_REQUIRE(d_pixel && d_next, "null hit list");
+    k_cosmic_chains<<<(n_hits + 127) / 128, 128, 0, st>>>(n_hits, d_pixel, n_pixels, d_head, d_next);
+    WB_LAUNCHED("k_cosmic_chains");
+    return WB200_OK;
+}
+
+int wb200_reads(const wb200_reads_args *a, void *stream)
+{
+    WB_REQUIRE(a != nullptr, "null args");
+    WB_REQUIRE(a->n_reads >= 1 && a->n_reads <= 15, "1 <= n_reads <= 15");
+    WB_REQUIRE(a->F > 2 * a->border && (a->F % 2) == 0, "F must be even and > 2*border");
+    WB_REQUIRE(a->d_dt && a->d_acc && a->d_out, "null buffer");
+    WB_REQUIRE(!a->add_sky || a->d_sky || a->d_draw_sky, "sky plane missing");
+    WB_REQUIRE(!a->add_dark || a->d_draw_dark || (a->d_dark && a->d_dark_err), "dark planes missing");
+    if (a->add_nonlinear)
+        for (int i = 0; i < 7; ++i)
+            WB_REQUIRE(a->d_nl[i], "non-linearity planes missing");
+    WB_REQUIRE(!a->d_cos_head || a->n_cosmics == 0 || (a->d_cos_next && a->d_cos_read && a->d_cos_energy),
+               "cosmic lists missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pairs = (size_t)a->F * a->F / 2;
+    const int blocks = (int)((pairs + 255) / 256);
+    if (a->exact_newton && a->add_nonlinear) {
+        WB_REQUIRE(!a->out_f32, "exact_newton needs the float64 output");
+        WB_REQUIRE(a->d_newton_iters, "newton scratch missing");
+        WB_CUDA(cudaMemsetAsync(a->d_newton_iters, 0, sizeof(int32_t) * 16, st));
+        k_reads<1><<<blocks, 256, 0, st>>>(*a);
+        WB_LAUNCHED("k_reads<1>");
+        k_reads<2><<<blocks, 256, 0, st>>>(*a);
+        WB_LAUNCHED("k_reads<2>");
+    } else {
+        k_reads<0><<<blocks, 256, 0, st>>>(*a);
+        WB_LAUNCHED("k_reads<0>");
+    }
+    return WB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PSF drop-in (wayne/pyparallel_menu.c:10-113): host buffers in, host frame out.
+// ---------------------------------------------------------------------------
+
+int wb200_psf_host(const int *counts, int size, const double *x_pos, const double *y_pos,
+                   const double *psf_ratio, const double *psf_sigmal, const double *psf_sigmah,
+                   int nr, int nc, int test, int threads, int rng_mode, const double *normals,
+                   int *frame_out)
+{
+    WB_REQUIRE(size >= 0 && nr > 0 && nc > 0 && frame_out, "bad sizes");
+    WB_REQUIRE(size == 0 || (counts && x_pos && y_pos && psf_ratio && psf_sigmal && psf_sigmah),
+               "null input");
+    WB_REQUIRE(rng_mode != WB200_RNG_HOST || normals, "normals missing");
+    WB_REQUIRE(rng_mode != WB200_RNG_RANDR || threads >= 1, "threads >= 1");
+    const size_t npix = (size_t)nr * nc;
+    if (size == 0) {
+        memset(frame_out, 0, npix * sizeof(int));
+        return WB200_OK;
+    }
+    long long ssum = 0;
+    for (int i = 0; i < size; ++i)
+        ssum += counts[i] > 0 ? counts[i] : 0;
+    WB_REQUIRE(ssum < 2147483647LL, "more than 2^31-1 electrons (the reference's int overflows too)");
+
+    const size_t nb = (size_t)size;
+    DevBuf d_counts, d_off, d_tot, d_dbl, d_win, d_misc, d_norm;
+    if (d_counts.alloc(nb * 4) || d_off.alloc(nb * 4) || d_tot.alloc(8) || d_dbl.alloc(nb * 8 * 5) ||
+        d_win.alloc(npix * 4) || d_misc.alloc(64))
+        return fail(WB200_ERR_NOMEM, "cudaMalloc failed%s%s");
+    cudaStream_t st = 0;
+    // negative counts never throw (the reference's loops simply do not run)
+    std::vector<int> cpos(counts, counts + size);
+    for (auto &c : cpos)
+        if (c < 0)
+            c = 0;
+    WB_CUDA(cudaMemcpyAsync(d_counts.p, cpos.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    double *dd = d_dbl.as<double>();
+    const double *src[5] = {x_pos, y_pos, psf_ratio, psf_sigmal, psf_sigmah};
+    for (int i = 0; i < 5; ++i)
+        WB_CUDA(cudaMemcpyAsync(dd + i * nb, src[i], nb * 8, cudaMemcpyHostToDevice, st));
+    const uint64_t tot = (uint64_t)ssum;
+    WB_CUDA(cudaMemcpyAsync(d_tot.p, &tot, 8, cudaMemcpyHostToDevice, st));
+    // misc: [0] lost (u64) [8] ox [12] oy [16] seed [24] normals_base (i64)
+    struct {
+        uint64_t lost;
+        int32_t ox, oy, seed, pad;
+        int64_t nbase;
+    } misc = {0, 0, 0, test, 0, 0};
+    WB_CUDA(cudaMemcpyAsync(d_misc.p, &misc, sizeof(misc), cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemsetAsync(d_win.p, 0, npix * 4, st));
+    if (rng_mode == WB200_RNG_HOST) {
+        if (d_norm.alloc((size_t)ssum * 2 * 8))
+            return fail(WB200_ERR_NOMEM, "cudaMalloc failed%s%s");
+        WB_CUDA(cudaMemcpyAsync(d_norm.p, normals, (size_t)ssum * 2 * 8, cudaMemcpyHostToDevice, st));
+    }
+    int rc = wb200_count_offsets(1, size, d_counts.as<int32_t>(), d_off.as<int32_t>(), st);
+    if (rc)
+        return rc;
+
+    wb200_photon_args a;
+    memset(&a, 0, sizeof(a));
+    a.n_samples = 1;
+    a.n_bins = size;
+    // enough CTAs to fill the machine, chunks a multiple of 32 bins
+    int chunk = ((size + 591) / 592 + 31) / 32 * 32;
+    a.chunk_bins = chunk < 32 ? 32 : chunk;
+    a.nr = nr;
+    a.nc = nc;
+    a.rng_mode = rng_mode;
+    a.threads = threads;
+    a.win_w = nc;
+    a.win_h = nr;
+    a.sub_scale = 0.0;
+    a.key0 = (uint32_t)test;
+    a.key1 = 0x57415945u; // "WAYE"
+    a.d_counts = d_counts.as<int32_t>();
+    a.d_offsets = d_off.as<int32_t>();
+    a.d_totals = d_tot.as<uint64_t>();
+    a.d_xpos = dd;
+    a.d_ypos = dd + nb;
+    a.d_ratio = dd + 2 * nb;
+    a.d_sigl = dd + 3 * nb;
+    a.d_sigh = dd + 4 * nb;
+    char *m = d_misc.as<char>();
+    a.d_lost = (uint64_t *)m;
+    a.d_win_ox = (int32_t *)(m + 8);
+    a.d_win_oy = (int32_t *)(m + 12);
+    a.d_seeds = (int32_t *)(m + 16);
+    a.d_normals_base = (int64_t *)(m + 24);
+    a.d_normals = d_norm.as<double>();
+    a.d_win = d_win.as<int32_t>();
+    rc = throw_photons(&a, 0, st);
+    if (rc)
+        return rc;
+    WB_CUDA(cudaMemcpyAsync(frame_out, d_win.p, npix * 4, cudaMemcpyDeviceToHost, st));
+    uint64_t lost = 0;
+    WB_CUDA(cudaMemcpyAsync(&lost, d_misc.p, 8, cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaStreamSynchronize(st));
+    if (lost)
+        return fail(WB200_ERR_LOST, "electrons fell outside the frame window%s%s");
+    return WB200_OK;
+}
+
+int *PSF(int *counts, int size, double *x_pos, double *y_pos, double *psf_ratio,
+         double *psf_sigmal, double *psf_sigmah, int nr, int nc, int test, int threads)
+{
+    if (nr <= 0 || nc <= 0) {
+        fail(WB200_ERR_ARG, "PSF: bad frame size%s%s");
+        return nullptr;
+    }
+    int *frame = (int *)malloc((size_t)nr * nc * sizeof(int)); // caller frees (pyparallel.pyx:36)
+    if (!frame) {
+        fail(WB200_ERR_NOMEM, "PSF: malloc failed%s%s");
+        return nullptr;
+    }
+    const int rc = wb200_psf_host(counts, size, x_pos, y_pos, psf_ratio, psf_sigmal, psf_sigmah, nr,
+                                  nc, test, threads, WB200_RNG_RANDR, nullptr, frame);
+    if (rc != WB200_OK) {
+        free(frame);
+        return nullptr;
+    }
+    return frame;
+}
+
+int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
+{
+    WB_REQUIRE(which >= 0 && which <= 7 && iters > 0 && ms_out && ops_out, "bad args");
+    cudaDeviceProp prop;
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    WB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8;
+    int *buf = nullptr;
+    const int n = 1 << 24; // 64 MB of ints
+    WB_CUDA(cudaMalloc(&buf, (size_t)n * 4));
+    WB_CUDA(cudaMemset(buf, 0, (size_t)n * 4));
+    cudaEvent_t e0, e1;
+    WB_CUDA(cudaEventCreate(&e0));
+    WB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        WB_CUDA(cudaEventRecord(e0));
+        if (which <= 3)
+            k_mb_smem_atomic<<<blocks, 256>>>(which, iters, buf);
+        else if (which <= 5)
+            k_mb_global_red<<<blocks, 256>>>(which, iters, buf, n);
+        else
+            k_mb_rng<<<blocks, 256>>>(which, iters, buf);
+        WB_LAUNCHED("microbench");
+        WB_CUDA(cudaEventRecord(e1));
+        WB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best)
+            best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *ms_out = best;
+    double ops = (double)blocks * 256.0 * iters;
+    if (which == 7)
+        ops *= 2.0; // two electrons (normal pairs) per Philox call
+    *ops_out = ops;
+    return WB200_OK;
+}
+
+} // extern "C"

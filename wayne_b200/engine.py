@@ -1,0 +1,465 @@
+"""Device engine: one exposure = one batched job on one B200.
+
+This is the host side of the hot path.  It owns device buffers as torch tensors
+(torch is used for nothing else), keeps the calibration planes resident in HBM
+per (grism, SUBARRAY, mode), and drives the stage kernels of libwayne_b200.so
+through ctypes, all on one CUDA stream with no host synchronisation until the
+result is copied back.
+
+Replaces the reference's serial per-sub-sample loop
+(wayne/exposure_generator.py:336-394) and its per-read / post-exposure numpy
+passes (:361-389, :407-444).  Policy (argument handling, RNG order of the
+compat mode, units) lives in exposure_generator.py; this module is mechanism.
+
+HBM layout (all row-major, float64 unless noted)
+  tables     wl, ratio, sigl, sigh, sens, dwl           [W]
+  trace      {x_ref,y_ref,m_t,c_t,m_w,c_w,m_wl,c_wl}    [N][8]
+  counts     int32                                      [N][W]
+  windows    int32, one per sub-sample of a batch       [nb][WH][WW]
+  acc        electrons per read interval, bordered      [R][F][F]
+  planes     sky, gain, zero, nl[7], dark/err[R]        [F][F] each (bordered)
+  out        the NSAMP reads                            [R+1][F][F]
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+BORDER = 5
+TILE_W, TILE_H = 128, 64            # must match csrc/wayne_b200.cu
+ZMAX = {_lib.RNG_PHILOX: 6.8, _lib.RNG_RANDR: 6.6}
+WINDOW_BYTES_CAP = 2 << 30          # HBM spent on sub-sample windows per batch
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.DP)
+
+
+class DeviceEngine(object):
+    """Per-GPU context: stream, resident calibration planes, scratch reuse."""
+
+    _engines = {}
+
+    @classmethod
+    def get(cls, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "wayne_b200 needs a CUDA device: the exposure path has no CPU implementation "
+                "(the CPU restatement under oracle/ is test infrastructure)")
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in cls._engines:
+            cls._engines[key] = cls(torch.device("cuda", key))
+        return cls._engines[key]
+
+    def __init__(self, device):
+        self.device = device
+        self._planes = {}
+
+    # -- helpers -----------------------------------------------------------
+    def stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_dev(self, a, dtype=None):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return torch.from_numpy(a).to(self.device, non_blocking=True)
+
+    def empty(self, shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def bordered(self, plane, F, fill=0.0):
+        """L x L host plane -> F x F float64 host plane with the 5-pixel border."""
+        plane = np.asarray(plane)
+        out = np.full((F, F), fill, dtype=np.float64)
+        n = plane.shape[0]
+        out[BORDER:BORDER + n, BORDER:BORDER + n] = plane
+        return out
+
+    def cached_plane(self, key, make):
+        if key not in self._planes:
+            self._planes[key] = make()
+        return self._planes[key]
+
+    def drop_planes(self):
+        self._planes.clear()
+
+
+class ExposureRun(object):
+    """One exposure's device state, built stage by stage."""
+
+    def __init__(self, engine, grism, subarray, wl_um, flux, depth, depth_col0, xr, yr, dur_ms,
+                 scale, read_end):
+        """
+        wl_um, flux [W]      cropped wavelength grid [micron] and stellar flux on it
+        depth [N][>=W] / None planet signal rows; columns depth_col0.. are used
+        xr, yr, dur_ms [N]   sub-sample reference positions [px] and durations [ms]
+        read_end [R]         index of the last sub-sample of each read
+        """
+        self.e = engine
+        self.grism = grism
+        self.S = int(subarray)
+        self.L = 1014 if self.S == 1024 else self.S
+        self.F = min(self.S + 10, 1024)
+        self.W = int(len(wl_um))
+        self.N = int(len(xr))
+        self.R = int(len(read_end))
+        self.sub_scale = float(507 - self.S // 2)     # exposure_generator.py:630 (py2 int division)
+        self.scale = 1.0 if scale is None else float(scale)
+        self.wl_host = np.ascontiguousarray(wl_um, dtype=np.float64)
+        self.xr_host = np.ascontiguousarray(xr, dtype=np.float64)
+        self.yr_host = np.ascontiguousarray(yr, dtype=np.float64)
+        self.read_end_host = np.ascontiguousarray(read_end, dtype=np.int32)
+        if self.W < 2:
+            raise ValueError("need at least two wavelength bins inside the grism limits")
+        if self.N < 1 or self.N > 65535:
+            raise ValueError("1..65535 sub-samples per exposure supported, got {}".format(self.N))
+
+        e = engine
+        st = e.stream_ptr()
+        self.d_wl = e.to_dev(self.wl_host)
+        self.d_flux = e.to_dev(flux, np.float64)
+        if depth is not None:
+            depth = np.asarray(depth)
+            if depth.dtype != np.float64 or not depth.flags.c_contiguous:
+                depth = np.ascontiguousarray(depth, dtype=np.float64)
+            self.d_depth_full = torch.from_numpy(depth).to(e.device, non_blocking=True)
+            self.depth_ld = int(depth.shape[1])
+            self.depth_ptr = C.c_void_p(self.d_depth_full.data_ptr() + 8 * int(depth_col0))
+        else:
+            self.d_depth_full, self.depth_ld, self.depth_ptr = None, 0, None
+        self.d_xr = e.to_dev(self.xr_host)
+        self.d_yr = e.to_dev(self.yr_host)
+        self.d_dur = e.to_dev(dur_ms, np.float64)
+        self.d_read_end = e.to_dev(self.read_end_host)
+
+        # ---- stage 1a: wavelength-only tables ---------------------------------
+        tabs = e.empty((5, self.W))
+        self.d_ratio, self.d_sigl, self.d_sigh, self.d_sens, self.d_dwl = tabs
+        poly = np.concatenate([np.asarray(grism.psf_ratio_poly.coeffs, dtype=np.float64),
+                               np.asarray(grism.psf_sigmal_poly.coeffs, dtype=np.float64),
+                               np.asarray(grism.psf_sigmah_poly.coeffs, dtype=np.float64)])
+        assert poly.shape == (12,)
+        self._poly = poly
+        sens_wl, sens_val = grism._load_sens()
+        key = ("sens", grism.name)
+        d_swl, d_sval = e.cached_plane(key, lambda: (e.to_dev(sens_wl), e.to_dev(sens_val)))
+        check(lib.wb200_bin_tables(self.W, _ptr(self.d_wl), _dp(poly), len(sens_wl), _ptr(d_swl),
+                                   _ptr(d_sval), _ptr(self.d_ratio), _ptr(self.d_sigl),
+                                   _ptr(self.d_sigh), _ptr(self.d_sens), _ptr(self.d_dwl), st),
+              "wb200_bin_tables")
+        # ---- stage 1b: trace per sub-sample -------------------------------------
+        self.d_trace = e.empty((self.N, _lib.TRACE_STRIDE))
+        a9 = np.asarray(grism.trace_coeff, dtype=np.float64)
+        b9 = np.asarray(grism.wl_solution, dtype=np.float64)
+        check(lib.wb200_trace_table(self.N, _ptr(self.d_xr), _ptr(self.d_yr), _dp(a9), _dp(b9),
+                                    _ptr(self.d_trace), st), "wb200_trace_table")
+        self.d_counts = None
+        self.d_totals = e.empty((self.N,), torch.int64)
+        self.d_expected = None
+        self.d_acc = None
+        self.lost = e.zeros((1,), torch.int64)
+
+    # ------------------------------------------------------------------
+    def tables_host(self):
+        """(ratio, sigl, sigh, sens, dwl) as numpy -- parity tests."""
+        return tuple(t.cpu().numpy() for t in
+                     (self.d_ratio, self.d_sigl, self.d_sigh, self.d_sens, self.d_dwl))
+
+    def trace_host(self):
+        return self.d_trace.cpu().numpy()
+
+    def positions_host(self):
+        e = self.e
+        xp = e.empty((self.N, self.W))
+        yp = e.empty((self.N, self.W))
+        check(lib.wb200_trace_positions(self.N, self.W, _ptr(self.d_trace), _ptr(self.d_wl),
+                                        self.sub_scale, _ptr(xp), _ptr(yp), e.stream_ptr()),
+              "wb200_trace_positions")
+        return xp.cpu().numpy(), yp.cpu().numpy()
+
+    # ------------------------------------------------------------------
+    def counts(self, mode, key=(0, 0), counts=None, want_expected=False):
+        """Stage 1c: expected electrons and their integer draw.
+
+        mode COUNT_NONE takes ``counts`` [N][W] from the caller (compat /
+        deterministic); COUNT_ROUND / COUNT_POISSON compute them on the device."""
+        e = self.e
+        if want_expected and self.d_expected is None:
+            self.d_expected = e.empty((self.N, self.W))
+        if mode == _lib.COUNT_NONE:
+            if counts is None:
+                raise ValueError("counts required")
+            c = np.ascontiguousarray(counts, dtype=np.int32)
+            if c.shape != (self.N, self.W):
+                raise ValueError("counts must be [N][W]")
+            self.d_counts = e.to_dev(c)
+        else:
+            self.d_counts = e.empty((self.N, self.W), torch.int32)
+        check(lib.wb200_counts(self.N, self.W, _ptr(self.d_flux), self.depth_ptr, self.depth_ld,
+                               _ptr(self.d_sens), _ptr(self.d_dwl), _ptr(self.d_dur), self.scale,
+                               mode, key[0] & 0xffffffff, key[1] & 0xffffffff,
+                               _ptr(self.d_expected) if want_expected else None,
+                               _ptr(self.d_counts), _ptr(self.d_totals), e.stream_ptr()),
+              "wb200_counts")
+
+    def expected_host(self):
+        if self.d_expected is None:
+            self.d_expected = self.e.empty((self.N, self.W))
+            check(lib.wb200_counts(self.N, self.W, _ptr(self.d_flux), self.depth_ptr,
+                                   self.depth_ld, _ptr(self.d_sens), _ptr(self.d_dwl),
+                                   _ptr(self.d_dur), self.scale, _lib.COUNT_NONE, 0, 0,
+                                   _ptr(self.d_expected), None, _ptr(self.d_totals),
+                                   self.e.stream_ptr()), "wb200_counts")
+        return self.d_expected.cpu().numpy()
+
+    # ------------------------------------------------------------------
+    def _window_geometry(self, zmax):
+        """Per-sub-sample HBM windows that are guaranteed to contain every
+        electron that lands inside the frame: trace extent +- zmax*sigma_max."""
+        g = self.grism
+        from .grism import wavelength_calibration_coeffs, ANGSTROM_TO_MICRON
+        x, y = self.xr_host, self.yr_host
+        m_t, c_t, m_w, c_w = wavelength_calibration_coeffs(x, y, g.trace_coeff, g.wl_solution)
+        X0, X1 = x + 10, x + 20
+        Y0 = m_t * (X0 - x) + c_t + y
+        Y1 = m_t * (X1 - x) + c_t + y
+        l0 = (m_w * np.sqrt((Y0 - y) ** 2 + (X0 - x) ** 2) + c_w) * ANGSTROM_TO_MICRON
+        l1 = (m_w * np.sqrt((Y1 - y) ** 2 + (X1 - x) ** 2) + c_w) * ANGSTROM_TO_MICRON
+        m_wl = (l1 - l0) / (X1 - X0)
+        c_wl = l0 - m_wl * X0
+        wl_lo, wl_hi = self.wl_host.min(), self.wl_host.max()
+        xa = (wl_lo - c_wl) / m_wl
+        xb = (wl_hi - c_wl) / m_wl
+        ya = m_t * (xa - x) + c_t + y
+        yb = m_t * (xb - x) + c_t + y
+        x_lo = np.minimum(xa, xb) - self.sub_scale
+        x_hi = np.maximum(xa, xb) - self.sub_scale
+        y_lo = np.minimum(ya, yb) - self.sub_scale
+        y_hi = np.maximum(ya, yb) - self.sub_scale
+        sig = max(float(np.abs(np.polyval(self._poly[8:12], self.wl_host)).max()),
+                  float(np.abs(np.polyval(self._poly[4:8], self.wl_host)).max()))
+        margin = int(math.ceil(zmax * sig)) + 2
+        L = self.L
+        ok = np.isfinite(x_lo) & np.isfinite(x_hi) & np.isfinite(y_lo) & np.isfinite(y_hi)
+        x_lo = np.where(ok, x_lo, 0.0)
+        x_hi = np.where(ok, x_hi, 0.0)
+        y_lo = np.where(ok, y_lo, 0.0)
+        y_hi = np.where(ok, y_hi, 0.0)
+        ox = np.clip(np.floor(x_lo).astype(np.int64) - margin, 0, L - 1)
+        oy = np.clip(np.floor(y_lo).astype(np.int64) - margin, 0, L - 1)
+        ex = np.clip(np.floor(x_hi).astype(np.int64) + margin + 1, 1, L)
+        ey = np.clip(np.floor(y_hi).astype(np.int64) + margin + 1, 1, L)
+        ww = int(max(1, (ex - ox).max()))
+        wh = int(max(1, (ey - oy).max()))
+        # chunk of bins whose trace segment plus 4 sigma fits the shared tile
+        extent = float(np.abs(x_hi - x_lo).max()) + 1.0
+        core = max(8.0, TILE_W - 2.0 * 4.0 * sig)
+        chunk = int(self.W * core / extent) if extent > core else self.W
+        chunk = max(32, chunk // 32 * 32)
+        want_ctas = 148 * 16
+        if self.N * math.ceil(self.W / chunk) < want_ctas:
+            per = max(1, want_ctas // self.N)
+            chunk = min(chunk, max(32, int(math.ceil(self.W / per / 32.0)) * 32))
+        return ox.astype(np.int32), oy.astype(np.int32), ww, wh, chunk
+
+    def throw(self, rng_mode, key=(0, 0), seeds=None, threads=1, normals=None, add_flat=True,
+              window_cap=WINDOW_BYTES_CAP):
+        """Stages 2+3 (+3b): throw and bin every electron, then flat-field and
+        accumulate into the per-read-interval planes ``acc``."""
+        e = self.e
+        st = e.stream_ptr()
+        N, W, L, F = self.N, self.W, self.L, self.F
+        if self.d_counts is None:
+            raise RuntimeError("counts() must run before throw()")
+        d_off = d_seeds = d_norm = d_nbase = None
+        if rng_mode == _lib.RNG_HOST:
+            normals = np.ascontiguousarray(normals, dtype=np.float64)
+            zmax = float(np.abs(normals[np.isfinite(normals)]).max()) * (1 + 1e-12) + 1e-9 \
+                if normals.size else 1.0
+        else:
+            zmax = ZMAX[rng_mode]
+        if rng_mode != _lib.RNG_PHILOX:
+            d_off = e.empty((N, W), torch.int32)
+            check(lib.wb200_count_offsets(N, W, _ptr(self.d_counts), _ptr(d_off), st),
+                  "wb200_count_offsets")
+        if rng_mode == _lib.RNG_RANDR:
+            d_seeds = e.to_dev(seeds, np.int32)
+        if rng_mode == _lib.RNG_HOST:
+            totals = self.d_totals.cpu().numpy()
+            base = np.zeros(N, dtype=np.int64)
+            base[1:] = np.cumsum(2 * totals[:-1])
+            if normals.size != int(2 * totals.sum()):
+                raise ValueError("normals must hold 2*sum(counts) values (x then y per sub-sample)")
+            d_norm = e.to_dev(normals)
+            d_nbase = e.to_dev(base)
+
+        ox, oy, ww, wh, chunk = self._window_geometry(zmax)
+        self.win_geometry = (ww, wh, chunk)
+        d_ox, d_oy = e.to_dev(ox), e.to_dev(oy)
+        per = ww * wh * 4
+        nb = int(max(1, min(N, window_cap // per)))
+        d_win = e.empty((nb, wh, ww), torch.int32)
+        if self.d_acc is None:
+            self.d_acc = e.zeros((self.R, F, F))
+        else:
+            self.d_acc.zero_()
+        self.lost.zero_()
+
+        g = self.grism
+        fl = g._load_flat() if add_flat else None
+        if add_flat:
+            d_flat = e.cached_plane(("flat", g.name, g.flat_file_name), lambda: tuple(
+                e.to_dev(p, np.float64) for p in fl['f']))
+        for s0 in range(0, N, nb):
+            n = min(nb, N - s0)
+            d_win[:n].zero_()
+            pa = _lib.PhotonArgs()
+            pa.n_samples, pa.n_bins, pa.chunk_bins = n, W, chunk
+            pa.nr, pa.nc = L, L
+            pa.rng_mode, pa.threads = rng_mode, int(threads)
+            pa.win_w, pa.win_h = ww, wh
+            pa.sub_scale = self.sub_scale
+            pa.key0, pa.key1 = key[0] & 0xffffffff, key[1] & 0xffffffff
+            pa.d_counts = self.d_counts.data_ptr() + 4 * s0 * W
+            pa.d_offsets = (d_off.data_ptr() + 4 * s0 * W) if d_off is not None else None
+            pa.d_totals = self.d_totals.data_ptr() + 8 * s0
+            pa.d_xpos = pa.d_ypos = None
+            pa.d_trace = self.d_trace.data_ptr() + 8 * _lib.TRACE_STRIDE * s0
+            pa.d_wl = self.d_wl.data_ptr()
+            pa.d_ratio, pa.d_sigl, pa.d_sigh = (self.d_ratio.data_ptr(), self.d_sigl.data_ptr(),
+                                                self.d_sigh.data_ptr())
+            pa.d_seeds = (d_seeds.data_ptr() + 4 * s0) if d_seeds is not None else None
+            pa.d_normals = d_norm.data_ptr() if d_norm is not None else None
+            pa.d_normals_base = (d_nbase.data_ptr() + 8 * s0) if d_nbase is not None else None
+            pa.d_win = d_win.data_ptr()
+            pa.d_win_ox = d_ox.data_ptr() + 4 * s0
+            pa.d_win_oy = d_oy.data_ptr() + 4 * s0
+            pa.d_lost = self.lost.data_ptr()
+            check(lib.wb200_throw_photons_at(C.byref(pa), s0, st), "wb200_throw_photons")
+
+            ga = _lib.GatherArgs()
+            ga.n_samples, ga.sample0, ga.n_reads = n, s0, self.R
+            ga.L, ga.F, ga.border = L, F, BORDER
+            ga.win_w, ga.win_h = ww, wh
+            ga.add_flat = 1 if add_flat else 0
+            ga.flat_off = g.flat_offset(self.S)
+            if add_flat:
+                ga.flat_n = int(fl['f'][0].shape[0])
+                ga.flat_wmin, ga.flat_wmax = float(fl['wmin']), float(fl['wmax'])
+                for i in range(4):
+                    ga.d_flat[i] = d_flat[i].data_ptr()
+            else:
+                ga.flat_n = 1014
+            ga.d_read_end = self.d_read_end.data_ptr()
+            ga.d_win = d_win.data_ptr()
+            ga.d_win_ox = d_ox.data_ptr() + 4 * s0
+            ga.d_win_oy = d_oy.data_ptr() + 4 * s0
+            ga.d_trace = self.d_trace.data_ptr() + 8 * _lib.TRACE_STRIDE * s0
+            ga.d_acc = self.d_acc.data_ptr()
+            check(lib.wb200_gather_flat(C.byref(ga), st), "wb200_gather_flat")
+        self._keep = (d_off, d_seeds, d_norm, d_nbase, d_ox, d_oy, d_win)
+        return self.d_acc
+
+    def check_lost(self):
+        n = int(self.lost.item())
+        if n:
+            raise _lib.WayneB200Error(
+                "{} electrons fell outside their sub-sample window (window bound violated)".format(n))
+
+    def photons(self):
+        """Electrons thrown in this exposure (incl. those landing off-frame)."""
+        return int(self.d_totals.sum().item())
+
+    # ------------------------------------------------------------------
+    def reads(self, dt_s, key=(0, 0), sky_rate=0.0, sky_plane=None, gain_plane=None, zero=None,
+              dark=None, nl_planes=None, noise=(0.0, 0.0), clip=None, read_noise=0.0,
+              cosmics=None, draws=None, exact_newton=False, out_f32=False, const_gain=2.35):
+        """Stage 4.  Planes are device tensors [F][F] (bordered) or None.
+
+        dark = (dark[R][F][F], err[R][F][F]) device tensors; cosmics =
+        (pixel[int32, bordered flat index], read[int32], energy[float64]) host arrays;
+        draws = dict of host arrays for the compat mode: 'noise' [R][L][L],
+        'sky' [R][L][L], 'dark' [R][F][F], 'rn' [R+1][F][F]."""
+        e = self.e
+        st = e.stream_ptr()
+        F, R = self.F, self.R
+        draws = draws or {}
+        a = _lib.ReadsArgs()
+        a.n_reads, a.F, a.border, a.out_f32 = R, F, BORDER, 1 if out_f32 else 0
+        a.add_noise = 1 if ('noise' in draws or (noise[0] and noise[1])) else 0
+        a.add_sky = 1 if ('sky' in draws or (sky_rate and sky_plane is not None)) else 0
+        a.add_dark = 1 if ('dark' in draws or dark is not None) else 0
+        a.add_nonlinear = 1 if nl_planes is not None else 0
+        a.clip = 1 if clip is not None else 0
+        a.add_read_noise = 1 if ('rn' in draws or read_noise) else 0
+        a.exact_newton = 1 if exact_newton else 0
+        a.key0, a.key1 = key[0] & 0xffffffff, key[1] & 0xffffffff
+        a.noise_mean, a.noise_std = float(noise[0] or 0.0), float(noise[1] or 0.0)
+        a.sky_rate = float(sky_rate or 0.0)
+        a.const_gain = float(const_gain)
+        a.clip_lo, a.clip_hi = (float(clip[0]), float(clip[1])) if clip is not None else (0.0, 0.0)
+        a.read_noise = float(read_noise or 0.0)
+        keep = []
+        d_dt = e.to_dev(dt_s, np.float64)
+        a.d_dt = d_dt.data_ptr()
+        a.d_acc = self.d_acc.data_ptr()
+        a.d_sky = sky_plane.data_ptr() if sky_plane is not None else None
+        a.d_gain = gain_plane.data_ptr() if gain_plane is not None else None
+        a.d_zero = zero.data_ptr() if zero is not None else None
+        if dark is not None:
+            a.d_dark, a.d_dark_err = dark[0].data_ptr(), dark[1].data_ptr()
+        if nl_planes is not None:
+            for i in range(7):
+                a.d_nl[i] = nl_planes[i].data_ptr()
+
+        def pad_stack(arr, n):
+            arr = np.asarray(arr, dtype=np.float64)
+            if arr.shape[-1] == F:
+                return np.ascontiguousarray(arr)
+            out = np.zeros((n, F, F))
+            m = arr.shape[-1]
+            out[:, BORDER:BORDER + m, BORDER:BORDER + m] = arr
+            return out
+
+        for name, field, n in (('noise', 'd_draw_noise', R), ('sky', 'd_draw_sky', R),
+                               ('dark', 'd_draw_dark', R), ('rn', 'd_draw_rn', R + 1)):
+            if name in draws:
+                t = e.to_dev(pad_stack(draws[name], n))
+                keep.append(t)
+                setattr(a, field, t.data_ptr())
+        if cosmics is not None and len(cosmics[0]):
+            pix, rd, en = cosmics
+            d_pix = e.to_dev(pix, np.int32)
+            d_rd = e.to_dev(rd, np.int32)
+            d_en = e.to_dev(en, np.float64)
+            d_head = e.empty((F * F,), torch.int32)
+            d_next = e.empty((len(pix),), torch.int32)
+            check(lib.wb200_cosmic_chains(len(pix), _ptr(d_pix), F * F, _ptr(d_head), _ptr(d_next),
+                                          st), "wb200_cosmic_chains")
+            a.n_cosmics = len(pix)
+            a.d_cos_head, a.d_cos_next = d_head.data_ptr(), d_next.data_ptr()
+            a.d_cos_read, a.d_cos_energy = d_rd.data_ptr(), d_en.data_ptr()
+            keep += [d_pix, d_rd, d_en, d_head, d_next]
+        d_iters = e.zeros((16,), torch.int32)
+        a.d_newton_iters = d_iters.data_ptr()
+        out = e.empty((R + 1, F, F), torch.float32 if out_f32 else torch.float64)
+        a.d_out = out.data_ptr()
+        check(lib.wb200_reads(C.byref(a), st), "wb200_reads")
+        self._keep_reads = keep + [d_dt, d_iters]
+        self.newton_iters = d_iters
+        return out
