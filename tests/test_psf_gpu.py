@@ -1,0 +1,113 @@
+"""GPU parity of the electron thrower (stages 2+3) through the C ABI:
+PSF / wb200_psf_host of libwayne_b200.so against the CPU oracle
+(oracle/psf_oracle.c, itself pinned to the unmodified reference).
+
+  compat  (rand_r stream reproduced on the GPU)  -> bit-exact int32 histogram
+  host    (caller-supplied normal table A)       -> bit-exact int32 histogram
+  philox  (native counter-based stream)          -> statistically equivalent
+"""
+import numpy as np
+import pytest
+
+from oracle import psf as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pyp():
+    from wayne_b200 import pyparallel
+    return pyparallel
+
+
+@pytest.mark.parametrize("test,threads", [(0, 1), (7, 2), (99999, 3), (123, 4), (5, 8), (31337, 16)])
+def test_compat_randr_bit_exact(pyp, test, threads):
+    case = O.psf_case(seed=test, n_bins=700, mean_count=35.0)
+    want = O.psf_port(test=test, threads=threads, **case)
+    got = pyp.psf_frame(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                        case["sigh"], case["nr"], case["nc"], test=test, threads=threads, rng='randr')
+    assert want.sum() > 0
+    assert np.array_equal(got, want)
+
+
+def test_apply_psf_signature_and_result(pyp):
+    """wayne.pyparallel.apply_psf drop-in: float64 [NR*NC], same numbers as the reference."""
+    case = O.psf_case(seed=9, n_bins=512, mean_count=50.0)
+    out = pyp.apply_psf(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                        case["sigh"], case["nr"], case["nc"], 4242, 2)
+    assert out.dtype == np.float64 and out.shape == (case["nr"] * case["nc"],)
+    want = O.psf_port(test=4242, threads=2, **case)
+    assert np.array_equal(out.reshape(case["nr"], case["nc"]), want.astype(np.float64))
+    ref = O.reference_pyparallel()
+    if ref is not None:   # the unmodified Cython module, when it was built
+        r = ref.apply_psf(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                          case["sigh"], case["nr"], case["nc"], 4242, 2)
+        assert np.array_equal(out, r)
+
+
+@pytest.mark.parametrize("frame,x0,x1,y0", [(256, 40.0, 200.0, 120.0), (64, -5.0, 70.0, 1.0),
+                                            (128, 100.0, 140.0, 126.5), (1014, 400.0, 600.0, 500.0)])
+def test_host_normals_bit_exact(pyp, frame, x0, x1, y0):
+    case = O.psf_case(seed=frame, n_bins=384, mean_count=60.0, frame=frame, x0=x0, x1=x1, y0=y0)
+    case["counts"][::5] = 0
+    ssum = int(case["counts"].sum())
+    A = np.random.default_rng(3).standard_normal(2 * ssum)
+    A[::1001] *= 3.0     # push some electrons far out (window / off-frame paths)
+    want = O.bin_electrons(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                           case["sigh"], frame, frame, A)
+    got = pyp.psf_frame(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                        case["sigh"], frame, frame, rng='host', normals=A)
+    assert np.array_equal(got, want)
+    assert got[0, :].sum() == 0 and got[:, 0].sum() == 0   # strict 0 < x, 0 < y
+
+
+def test_large_subsample_bit_exact(pyp):
+    """One config-1-sized sub-sample: 4494 bins, ~5e5 electrons."""
+    case = O.psf_case(seed=77, n_bins=4494, mean_count=110.0, frame=256, x0=44.6, x1=215.7, y0=79.7)
+    want = O.psf_port(test=1963, threads=2, **case)
+    got = pyp.psf_frame(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                        case["sigh"], 256, 256, test=1963, threads=2, rng='randr')
+    assert np.array_equal(got, want)
+
+
+def test_empty_inputs(pyp):
+    case = O.psf_case(seed=1, n_bins=64)
+    case["counts"][:] = 0
+    got = pyp.psf_frame(case["counts"], case["x"], case["y"], case["ratio"], case["sigl"],
+                        case["sigh"], 256, 256, rng='randr')
+    assert got.sum() == 0
+    z = np.zeros(0)
+    got = pyp.psf_frame(np.zeros(0, np.int32), z, z, z, z, z, 32, 32, rng='randr')
+    assert got.shape == (32, 32) and got.sum() == 0
+
+
+def test_philox_statistics(pyp):
+    """Native stream: same distribution as the reference's (mean profile and
+    per-pixel variance), electrons conserved, deterministic per key."""
+    case = O.psf_case(seed=5, n_bins=512, mean_count=400.0)
+    args = (case["counts"], case["x"], case["y"], case["ratio"], case["sigl"], case["sigh"], 256, 256)
+    a = pyp.psf_frame(*args, test=1, rng='philox')
+    b = pyp.psf_frame(*args, test=1, rng='philox')
+    c = pyp.psf_frame(*args, test=2, rng='philox')
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, c)
+    total = int(case["counts"].sum())
+    assert 0.995 * total < a.sum() <= total        # the trace is well inside the frame
+    # mean over seeds vs the oracle's mean over seeds, per column and per row
+    n = 24
+    gp = np.zeros((256, 256))
+    cp = np.zeros((256, 256))
+    for s in range(n):
+        gp += pyp.psf_frame(*args, test=100 + s, rng='philox')
+        cp += O.psf_port(test=100 + s, threads=1, **case)
+    for axis in (0, 1):
+        g, r = gp.sum(axis=axis), cp.sum(axis=axis)
+        sel = r > 50 * n
+        z = (g[sel] - r[sel]) / np.sqrt(g[sel] + r[sel])
+        assert np.abs(z).max() < 5.0, z
+        assert abs(z.mean()) < 0.5
+    # core/wing split: fraction of electrons within 2 px of the trace row
+    rows = np.arange(256)[:, None]
+    core = np.abs(rows - 121) <= 2
+    fg, fr = gp[core.repeat(256, 1)].sum() / gp.sum(), cp[core.repeat(256, 1)].sum() / cp.sum()
+    assert abs(fg - fr) < 2e-3
