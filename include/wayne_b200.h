@@ -194,6 +194,10 @@ typedef struct wb200_gather_args {
     int32_t add_flat;
     int32_t flat_off;           /* (1014 - SUBARRAY) floor-div 2 (grism.py:361) */
     int32_t flat_n;             /* side of the flat planes (1014)              */
+    int32_t flat_f32;           /* 1: round the flat value to float32 before it */
+                                /* multiplies -- the reference stores it in    */
+                                /* np.ones_like(flat_f0), the FITS float32     */
+                                /* dtype (grism.py:380-385)                    */
     double flat_wmin, flat_wmax;
     const int32_t *d_read_end;  /* [R] global index of each read's last sample */
     const int32_t *d_win;
@@ -228,6 +232,8 @@ typedef struct wb200_reads_args {
     uint32_t key0, key1;
     double noise_mean, noise_std;   /* per second (exposure_generator.py:477-479) */
     double sky_rate;            /* counts/s                                     */
+    int32_t sky_f32;            /* 1: Poisson mean = float32(sky)*float32(rate*dt), */
+    int32_t pad0;               /* the in-place float32 product of :489-493     */
     double const_gain;          /* 2.35, used when d_gain == NULL               */
     double clip_lo, clip_hi;    /* -20, 78000                                   */
     double read_noise;          /* 14.1/2.35                                    */

@@ -50,6 +50,7 @@ class GatherArgs(C.Structure):
         ("L", c_i32), ("F", c_i32), ("border", c_i32),
         ("win_w", c_i32), ("win_h", c_i32),
         ("add_flat", c_i32), ("flat_off", c_i32), ("flat_n", c_i32),
+        ("flat_f32", c_i32),
         ("flat_wmin", c_double), ("flat_wmax", c_double),
         ("d_read_end", c_void_p), ("d_win", c_void_p), ("d_win_ox", c_void_p),
         ("d_win_oy", c_void_p), ("d_trace", c_void_p),
@@ -66,6 +67,7 @@ class ReadsArgs(C.Structure):
         ("exact_newton", c_i32), ("n_cosmics", c_i32),
         ("key0", c_u32), ("key1", c_u32),
         ("noise_mean", c_double), ("noise_std", c_double), ("sky_rate", c_double),
+        ("sky_f32", c_i32), ("pad0", c_i32),
         ("const_gain", c_double), ("clip_lo", c_double), ("clip_hi", c_double),
         ("read_noise", c_double),
         ("d_dt", c_void_p), ("d_acc", c_void_p), ("d_sky", c_void_p), ("d_gain", c_void_p),

@@ -118,7 +118,10 @@ __global__ void __launch_bounds__(GX * GY) k_gather(const wb200_gather_args a)
                     f3 = a.d_flat[3][fidx];
                     have_f = true;
                 }
-                v = v * flat_value(g, Xd, Yd, f0, f1, f2, f3, a.flat_wmin, a.flat_wmax);
+                double fv = flat_value(g, Xd, Yd, f0, f1, f2, f3, a.flat_wmin, a.flat_wmax);
+                if (a.flat_f32)
+                    fv = (double)__double2float_rn(fv); // stored in ones_like(flat_f0)
+                v = v * fv;
             }
             acc = acc + v;
             touched = true;

@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                                 px = px + ds[h];
                             } else {
                                 PhiloxStream g(a.key0, a.key1, pid, (uint32_t)r, WB_STREAM_SKY);
-                                px = px + (double)poisson_draw(g, sky[h] * (a.sky_rate * dt));
+                                const double bg = a.sky_rate * dt;
+                                const double lam = a.sky_f32
+                                    ? (double)__fmul_rn(__double2float_rn(sky[h]), __double2float_rn(bg))
+                                    : sky[h] * bg;
+                                px = px + (double)poisson_draw(g, lam);
                             }
                         }
                         if (chead[h] >= 0) {

@@ -360,6 +360,7 @@ class ExposureRun(object):
             ga.flat_off = g.flat_offset(self.S)
             if add_flat:
                 ga.flat_n = int(fl['f'][0].shape[0])
+                ga.flat_f32 = 1 if fl['f'][0].dtype.itemsize == 4 else 0
                 ga.flat_wmin, ga.flat_wmax = float(fl['wmin']), float(fl['wmax'])
                 for i in range(4):
                     ga.d_flat[i] = d_flat[i].data_ptr()
@@ -388,7 +389,8 @@ class ExposureRun(object):
     # ------------------------------------------------------------------
     def reads(self, dt_s, key=(0, 0), sky_rate=0.0, sky_plane=None, gain_plane=None, zero=None,
               dark=None, nl_planes=None, noise=(0.0, 0.0), clip=None, read_noise=0.0,
-              cosmics=None, draws=None, exact_newton=False, out_f32=False, const_gain=2.35):
+              cosmics=None, draws=None, exact_newton=False, out_f32=False, const_gain=2.35,
+              sky_f32=True):
         """Stage 4.  Planes are device tensors [F][F] (bordered) or None.
 
         dark = (dark[R][F][F], err[R][F][F]) device tensors; cosmics =
@@ -411,6 +413,7 @@ class ExposureRun(object):
         a.key0, a.key1 = key[0] & 0xffffffff, key[1] & 0xffffffff
         a.noise_mean, a.noise_std = float(noise[0] or 0.0), float(noise[1] or 0.0)
         a.sky_rate = float(sky_rate or 0.0)
+        a.sky_f32 = 1 if sky_f32 else 0
         a.const_gain = float(const_gain)
         a.clip_lo, a.clip_hi = (float(clip[0]), float(clip[1])) if clip is not None else (0.0, 0.0)
         a.read_noise = float(read_noise or 0.0)

@@ -16,6 +16,10 @@ _calb_dir = os.environ.get("WAYNE_CALB_DIR",
 
 seed = None  # set by the visit driver (wayne/params.py:60, run_visit.py:69-77)
 
+# default random-stream mode of ExposureGenerator: 'philox' (native, counter
+# based) or 'numpy' (compat: the reference's numpy + rand_r streams)
+rng = os.environ.get("WAYNE_B200_RNG", "philox")
+
 
 def set_calibration_dir(path):
     """Point the package at a calibration directory (affects objects built afterwards)."""
