@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- exposures/s and photons/s of the exposure-synthesis path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--workload c4|c1|tiny]
+
+A "step" is one full exposure (stages 1-4: trace/dispersion/sensitivity, Philox
+Poisson counts, electron throw + binning, flat-field gather, fused per-pixel
+ramp pass).  Workload at N=1 = BASELINE.json configs[3], the configuration the
+metric is quoted on: G141 spatial scan, 1024^2 full frame, NSAMP=15 RAPID,
+10 ms sub-samples (4110 of them), 4096 wavelength bins, ~1e9 photons.
+
+  value   exposures/s with the exposure's inputs already resident in HBM and the
+          reads left in HBM (CUDA events on the launching stream, max over ranks)
+  e2e     the same through ExposureGenerator.scanning_frame with HOST buffers:
+          pinned host->device copy of the inputs and device->host copy of the
+          NSAMP reads inside the timed region
+  roofline / roofline_hbm   per-kernel, durations from CUDA events recorded around
+          each launch inside the timed region
+  cpu_baseline   the oracle (unmodified reference C kernel when it was compiled
+          in the build container, else the C port) + numpy restatement, timed on
+          this host on a bounded sample of the same exposure
+
+N > 1 (torchrun): exposures are independent, so every rank runs its own
+exposures (weak scaling, no data-path collective); value = all ranks' exposures
+/ max-over-ranks time.
+
+--impl reference: the reference's CPU path (oracle/) alone, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: grism, SUBARRAY, NSAMP, SAMPSEQ, scan px/s, sample ms, W, photons, x_ref, y_ref
+    'c4': dict(grism='G141', sub=1024, nsamp=15, seq='RAPID', scan=20.0, rate=10.0, W=4096,
+               photons=1.0e9, x_ref=330.0, y_ref=110.0,
+               desc='configs[3]: G141 spatial scan 1024x1024 full frame, NSAMP=15 RAPID (41.05 s), '
+                    '20 px/s, 10 ms sub-samples, 4096 wavelength bins, ~1e9 photons/exposure, '
+                    'flat+sky+cosmics+gain+dark+non-linearity+clip+read noise on, SSVSine, visit trend'),
+    'c1': dict(grism='G141', sub=256, nsamp=5, seq='SPARS10', scan=7.4325, rate=10.0, W=4494,
+               photons=3.0e8, x_ref=404.497, y_ref=457.427,
+               desc='configs[0]-shaped: G141 scan 256 subarray NSAMP=5 SPARS10, 2233 sub-samples x 4494 bins'),
+    'tiny': dict(grism='G141', sub=256, nsamp=5, seq='SPARS10', scan=7.4325, rate=200.0, W=512,
+                 photons=2.0e6, x_ref=404.497, y_ref=457.427, desc='smoke-sized scan'),
+}
+
+
+def calibration_dir(wk):
+    from wayne_b200 import calibration, params
+    d = os.environ.get('WAYNE_CALB_DIR') or os.path.join(tempfile.gettempdir(), 'wayne_b200_synth_calb')
+    rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if rank == 0:
+        calibration.write_synthetic_calibration(d, modes=((wk['sub'], wk['seq']),))
+        open(os.path.join(d, '.ready_%s_%s' % (wk['sub'], wk['seq'])), 'w').close()
+    else:
+        while not os.path.exists(os.path.join(d, '.ready_%s_%s' % (wk['sub'], wk['seq']))):
+            time.sleep(0.2)
+    params.set_calibration_dir(d)
+    return d
+
+
+def make_inputs(wk, exposure_index=0):
+    """Host inputs of one exposure of the workload (seeded, synthetic)."""
+    from wayne import detector, grism
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator
+    g = grism.G141() if wk['grism'] == 'G141' else grism.G102()
+    det = detector.WFC3_IR()
+    eg = ExposureGenerator(det, g, wk['nsamp'], wk['seq'], wk['sub'], None)
+    _, mid, dur, ri = eg._gen_scanning_sample_times(wk['rate'] * u.ms)
+    lo, hi = (float(u.value_in(v, u.micron)) for v in g.wl_limits)
+    wl = np.exp(np.linspace(np.log(lo), np.log(hi), wk['W']))       # log-spaced, all inside the limits
+    rng = np.random.default_rng(20170410)
+    x = 1.4388e4 / (wl * 6065.0)
+    bb = 1.0 / (wl ** 5 * (np.exp(x) - 1.0))
+    flux = bb / bb.max() * (1 + 0.01 * rng.standard_normal(len(wl)))
+    # scale to the target photon count: sum over (sample, bin) of expected electrons
+    sens_wl, sens_val = g._load_sens()
+    from wayne import tools
+    per_ms = flux * np.interp(wl, sens_wl, sens_val) * tools.bin_centers_to_widths(wl) * 1e4 * 1e-3
+    total = per_ms.sum() * float(np.sum(u.value_in(dur, u.ms)))
+    flux = flux * (wk['photons'] / total)
+    depth0 = 0.0146 * (1 + 0.01 * np.sin(12 * wl))
+    lc = 0.5 * (1 + np.tanh((np.linspace(-1, 1, len(mid)) + 0.2 * exposure_index) * 3))
+    return dict(eg_args=(det, g, wk['nsamp'], wk['seq'], wk['sub'], None), wl=wl, flux=flux,
+                depth0=depth0, lightcurve=lc, mid=mid, dur=dur, read_index=ri,
+                read_times=np.asarray(u.value_in(eg.read_times, u.s), dtype=float))
+
+
+def frame_kwargs(wk, i):
+    from wayne import units as u
+    from wayne.trend_generators.scan_speed_varations import SSVSine
+    rw = np.random.default_rng(1963 + i)
+    return dict(x_ref=wk['x_ref'] + 0.02 * rw.standard_normal(), y_ref=wk['y_ref'] + 0.02 * rw.standard_normal(),
+                x_jitter=0.025, y_jitter=0.025, scan_speed=wk['scan'] * u.pixel / u.s,
+                sample_rate=wk['rate'] * u.ms, ssv_generator=SSVSine(1.5, 1.1, 0), cosmic_rate=11.,
+                sky_background=5.5 * u.count / u.s, scale_factor=1.0 - 1e-4 * i)
+
+
+class ClockSampler(object):
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(mx)) if mx else None, 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm (oracle/): bounded sample of the same exposure
+# ---------------------------------------------------------------------------
+def cpu_reference_exposure(wk, inp, n_sub, threads=None):
+    """Time the reference's CPU path on ``n_sub`` evenly spread sub-samples plus
+    ALL read reductions and the post-exposure chain; extrapolate the sub-sample
+    part to the exposure's N sub-samples.  Returns (seconds per exposure, info)."""
+    from oracle import exposure_oracle as E
+    from oracle import psf as OP
+    from tests import harness
+    kind = 'reference' if OP.have_reference() else 'port'
+    cal = harness.oracle_calibration(wk['grism'], dark_mode=(wk['sub'], wk['seq']), nsamp=wk['nsamp'])
+    from wayne import units as u
+    mid = np.asarray(u.value_in(inp['mid'], u.ms))
+    dur = np.asarray(u.value_in(inp['dur'], u.ms))
+    ri = inp['read_index']
+    N = len(mid)
+    # evenly spread sub-samples, at least one per read, each read closed by its last pick
+    picks, new_ri, first = [], [], 0
+    per_read = max(1, n_sub // len(ri))
+    for last in ri:
+        idx = np.unique(np.linspace(first, last, per_read).round().astype(int))
+        picks.extend(idx.tolist())
+        new_ri.append(len(picks) - 1)
+        first = last + 1
+    picks = np.array(picks)
+    depth = inp['depth0'][None, :] * inp['lightcurve'][picks][:, None]
+    ncpu = os.cpu_count() or 1
+    if threads is None:
+        if kind == 'reference':
+            # the reference's OpenMP team only speeds up the normal table: pick
+            # the best team size on one sub-sample
+            best, threads = None, 1
+            for t in [t for t in (1, 2, 4, 8, 16) if t <= ncpu]:
+                t0 = time.perf_counter()
+                E.scanning_frame(cal, wk['grism'], wk['sub'], inp['read_times'][:1], inp['wl'], inp['flux'],
+                                 None, wk['x_ref'], wk['y_ref'], 0.0, 0.0, 0.0, wk['rate'],
+                                 np.random.RandomState(1), add_dark=False, sky_background=0,
+                                 add_non_linear=False, add_read_noise=False, threads=t, psf=kind,
+                                 sample_times=(mid[:2], dur[:2], [1]))
+                el = time.perf_counter() - t0
+                if best is None or el < best:
+                    best, threads = el, t
+        else:
+            threads = 1
+    kw = frame_kwargs(wk, 0)
+    t0 = time.perf_counter()
+    o = E.scanning_frame(cal, wk['grism'], wk['sub'], inp['read_times'], inp['wl'], inp['flux'], depth,
+                         kw['x_ref'], kw['y_ref'], 0.025, 0.025, wk['scan'] * 0.001, wk['rate'],
+                         np.random.RandomState(1963), ssv=(1.5, 1.1, 0), cosmic_rate=11.,
+                         sky_background=5.5, scale_factor=kw['scale_factor'], threads=threads, psf=kind,
+                         sample_times=(mid[picks], dur[picks], new_ri))
+    wall = time.perf_counter() - t0
+    tm = o['timing']
+    per_exposure = tm['subsamples'] * (N / float(len(picks))) + tm['reads'] + tm['post']
+    photons = o['photons'] * (N / float(len(picks)))
+    info = {'kind': kind, 'cores': int(threads),
+            'sample': '%d of %d sub-samples (evenly spread) + all %d read reductions + post-exposure chain, '
+                      'sub-sample time scaled by %d/%d; %.1f s of CPU work' % (
+                          len(picks), N, len(ri), N, len(picks), wall),
+            'seconds_per_exposure': per_exposure, 'photons_per_exposure': photons}
+    return per_exposure, info
+
+
+def run_reference(args, wk):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    calibration_dir(wk)
+    inp = make_inputs(wk)
+    n_sub = 6 * len(inp['read_index'])
+    times, info = [], None
+    for i in range(args.warmup + args.steps):
+        t, info = cpu_reference_exposure(wk, inp, n_sub if i >= args.warmup else len(inp['read_index']),
+                                         threads=info['cores'] if info else None)
+        if i >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    val = 1.0 / sec
+    line = {'impl': 'reference', 'metric': 'exposures_per_s', 'value': val, 'unit': 'exposures/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'photons_per_s': info['photons_per_exposure'] / sec,
+            'config': {'workload': wk['desc'], 'rng': 'numpy+rand_r (reference streams)'},
+            'cpu_baseline': {'value': val, 'unit': 'exposures/s', 'cores': info['cores'],
+                             'kind': info['kind'], 'sample': info['sample']},
+            'e2e': {'value': val, 'unit': 'exposures/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------
+def run_native(args, wk):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    calibration_dir(wk)
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator
+    from wayne_b200 import _lib
+    from wayne_b200.engine import DeviceEngine
+    eng = DeviceEngine.get(local)
+    inp = make_inputs(wk)
+    N, W = len(inp['read_index']) and len(np.asarray(u.value_in(inp['mid'], u.ms))), len(inp['wl'])
+
+    # host inputs in pinned memory (e2e leg) and a device-resident copy (value leg)
+    depth_pin = torch.empty((N, W), dtype=torch.float64, pin_memory=True)
+    depth_host = depth_pin.numpy()
+    depth_host[:] = inp['depth0'][None, :] * inp['lightcurve'][:, None]
+    depth_dev = depth_pin.to(dev)
+    wl_q = inp['wl'] * u.micron
+
+    def one(i, resident):
+        eg = ExposureGenerator(*inp['eg_args'], filename='%04d_raw.fits' % (i + 1), rng='philox', device=local)
+        kw = frame_kwargs(wk, rank * 100000 + i)
+        exp = eg.scanning_frame(kw.pop('x_ref'), kw.pop('y_ref'), kw.pop('x_jitter'), kw.pop('y_jitter'),
+                                wl_q, inp['flux'], depth_dev if resident else depth_host,
+                                kw.pop('scan_speed'), kw.pop('sample_rate'), inp['mid'], inp['dur'],
+                                inp['read_index'], rng_key=(1963, rank * 100000 + i),
+                                device_result=resident, **kw)
+        return eg, exp
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident inputs, CUDA events on the launching stream ----
+    for i in range(args.warmup):
+        one(i, True)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.profile = True
+    eng.stage_times()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream(dev)
+    e0.record(st)
+    runs = []
+    for i in range(args.steps):
+        eg, _ = one(args.warmup + i, True)
+        runs.append(eg._run)
+    e1.record(st)
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms_value = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    stages = eng.stage_times()
+    eng.profile = False
+    clocks = sampler.stop() if sampler else None
+    photons = float(np.mean([r.photons() for r in runs]))
+    for r in runs:
+        r.check_lost()
+    geom = runs[-1].win_geometry
+    del runs
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside ---------------
+    for i in range(max(1, args.warmup // 2)):
+        one(i, False)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        eg, exp = one(args.warmup + i, False)
+        d2h = sum(r[0].nbytes for r in exp.reads)
+        del exp
+    torch.cuda.synchronize(dev)
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    h2d = depth_host.nbytes + inp['flux'].nbytes + inp['wl'].nbytes + 3 * 8 * N
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the per-kernel durations measured above ------------------------
+    S = wk['sub']
+    F = min(S + 10, 1024)
+    R = wk['nsamp'] - 1
+    per = lambda name: (stages[name][0] / args.steps) if name in stages else None   # noqa: E731
+    hbm_peak, peak_src = measured_peaks()
+    reads_bytes = (R * F * F * 8            # interval accumulators
+                   + 2 * R * F * F * 8      # dark, dark error
+                   + 2 * F * F * 8          # sky, gain
+                   + 7 * F * F * 8          # non-linearity planes
+                   + (F * F * 8 if S == 256 else 0) + F * F * 4   # zero read, cosmic heads
+                   + (R + 1) * F * F * 8)   # NSAMP reads written
+    t_reads, t_throw, t_gather, t_counts = per('k_reads'), per('k_throw'), per('k_gather'), per('k_counts')
+    ww, wh, chunk = geom
+    gather_bytes = N * ww * wh * 4 + 2 * R * F * F * 8
+    roof_hbm = {'kernel': 'k_reads<0>', 'bound': 'hbm', 'achieved': reads_bytes / (t_reads * 1e-3) / 1e9,
+                'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': peak_src,
+                'frac': reads_bytes / (t_reads * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
+                'algorithmic_bytes': reads_bytes, 'ms': t_reads}
+    smem_peak = None
+    try:
+        import ctypes as C
+        ms, ops = C.c_double(), C.c_double()
+        _lib.check(_lib.lib.wb200_microbench(0, 4096, C.byref(ms), C.byref(ops)), 'microbench')
+        smem_peak = ops.value / (ms.value * 1e-3) / 1e9
+    except Exception:
+        pass
+    roof_throw = {'kernel': 'k_throw<PHILOX>', 'bound': 'smem_atomic', 'achieved': photons / (t_throw * 1e-3) / 1e9,
+                  'peak': smem_peak, 'unit': 'Gphoton/s (1 shared-memory atomic increment per photon)',
+                  'peak_source': 'wb200_microbench(0): conflict-free shared atomicAdd, all SMs, measured in this run',
+                  'frac': (photons / (t_throw * 1e-3) / 1e9 / smem_peak) if smem_peak else None,
+                  'traffic': None, 'ms': t_throw}
+    dominant = max(stages.items(), key=lambda kv: kv[1][0])[0]
+    line = {
+        'metric': 'exposures_per_s', 'value': world * 1e3 / ms_value, 'unit': 'exposures/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'photons_per_exposure': photons,
+        'photons_per_s': world * photons * 1e3 / ms_value,
+        'config': {'workload': wk['desc'], 'n_subsamples': N, 'n_bins': W, 'rng': 'philox',
+                   'out_dtype': 'float64', 'window': [ww, wh], 'chunk_bins': chunk,
+                   'l2': 'no flush: per-exposure working set (windows+planes+reads, > 500 MB) exceeds the 126 MB L2'},
+        'clocks': clocks,
+        'e2e': {'value': world * 1e3 / ms_e2e, 'unit': 'exposures/s', 'ms_per_step': ms_e2e,
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(launches),
+        'stage_ms': {k: v[0] / args.steps for k, v in stages.items()},
+        'dominant_kernel': dominant,
+        'roofline': roof_throw if dominant == 'k_throw' else roof_hbm,
+        'roofline_hbm': roof_hbm,
+        'roofline_photons': roof_throw,
+        'gather': {'ms': t_gather, 'algorithmic_bytes': gather_bytes,
+                   'achieved_gbs': gather_bytes / (t_gather * 1e-3) / 1e9 if t_gather else None},
+    }
+    if world == 1 and not args.no_cpu:
+        sec, info = cpu_reference_exposure(wk, inp, 4 * len(inp['read_index']))
+        line['cpu_baseline'] = {'value': 1.0 / sec, 'unit': 'exposures/s', 'cores': info['cores'],
+                                'kind': info['kind'], 'sample': info['sample'],
+                                'photons_per_s': info['photons_per_exposure'] / sec}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=('native', 'reference'))
+    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    wk = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        if args.steps > 3:
+            args.steps = 3          # bounded: each step is ~10-20 s of CPU work
+        args.warmup = min(args.warmup, 1)
+        run_reference(args, wk)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_native(args, wk)
+
+
+if __name__ == '__main__':
+    main()

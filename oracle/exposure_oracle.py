@@ -22,6 +22,8 @@ numpy version note: the reference pins numpy 1.14 (README.md:26), i.e. legacy
 value-based casting.  Where that changes an expression's working precision it
 is written out explicitly below instead of relying on the numpy in this image.
 """
+import time as _time
+
 import numpy as np
 
 from . import psf as _psf
@@ -261,7 +263,7 @@ def reset_reference_pixels(a):
 
 
 class Draws(object):
-    """Source of the numpy-side random numbers, in the reference's order (A.7).
+    """(unused placeholder) Source of the numpy-side random numbers, in the reference's order (A.7).
     Default: a legacy RandomState (the reference uses the global one)."""
 
     def __init__(self, seed):
@@ -319,7 +321,9 @@ def scanning_frame(cal, grism, subarray, read_times_s, wl_um, stellar_flux, plan
     all_counts = np.zeros((N, len(s_wl)), dtype=np.int64) if keep else None
     photons = 0
     read_num, prev_t = 0, 0.0
+    timing = {'subsamples': 0.0, 'reads': 0.0, 'post': 0.0}
     for i in range(N):
+        _t0 = _time.perf_counter()
         depth = planet_signal[i][i0:i1] if planet_signal is not None else None
         sx, sy = x_ref + jx[i], s_y_refs[i] + jy[i]              # :355-356
         tr = Trace(sx, sy, a, b)
@@ -340,8 +344,10 @@ def scanning_frame(cal, grism, subarray, read_times_s, wl_um, stellar_flux, plan
         if add_flat:
             frame = flat_field_at_hits(sx, sy, S, frame, cal, a, b)   # :641-645
         pixel_array += frame                                     # :359
+        timing['subsamples'] += _time.perf_counter() - _t0
 
         if i in read_index:                                      # :361
+            _t0 = _time.perf_counter()
             dt = read_times_s[read_num] - prev_t                 # :363-365
             px = pixel_array
             if noise_mean and noise_std:                         # :477-484
@@ -365,6 +371,8 @@ def scanning_frame(cal, grism, subarray, read_times_s, wl_um, stellar_flux, plan
             prev_t = read_times_s[read_num]
             read_num += 1
             pixel_array = np.zeros((L, L))                       # :388
+            timing['reads'] += _time.perf_counter() - _t0
+    _t0 = _time.perf_counter()
     assert len(reads) == len(read_times_s) + 1                   # :397
 
     newton_iters = []
@@ -384,6 +392,7 @@ def scanning_frame(cal, grism, subarray, read_times_s, wl_um, stellar_flux, plan
         reads[r] = reads[r] + reads[0]
     if add_read_noise:                                           # exposure.py:61-68, detector.py:193-198
         reads = [rs.normal(r, READ_NOISE) for r in reads]
-    return dict(reads=reads, seeds=seeds, jitter=(jx, jy), durations=dur, s_y_refs=s_y_refs,
+    timing['post'] = _time.perf_counter() - _t0
+    return dict(reads=reads, timing=timing, seeds=seeds, jitter=(jx, jy), durations=dur, s_y_refs=s_y_refs,
                 read_index=read_index, counts=all_counts, photons=photons,
                 newton_iters=newton_iters, wl=s_wl, crop=(i0, i1))

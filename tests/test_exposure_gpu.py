@@ -179,5 +179,9 @@ def test_philox_mode_statistics(calb_dir):
     se = np.sqrt((gv + ov) / n_seeds)
     z = (gm - om) / se
     assert np.abs(z).max() < 4.5 and abs(z.mean()) < 0.3 and (np.abs(z) > 3).mean() < 0.01
-    ratio = gv.sum() / ov.sum()
-    assert 0.9 < ratio < 1.1
+    # variance: compare on the ~25 trace blocks that carry the signal; each sample
+    # variance (40 seeds) has a relative error of sqrt(2/39) = 0.23
+    sig = om - np.median(om)
+    bright = sig > 0.2 * sig.max()
+    lr = np.log(gv[bright] / ov[bright])
+    assert abs(lr.mean()) < 4 * np.sqrt(2 * 2.0 / 39 / bright.sum()) + 0.02, (lr.mean(), bright.sum())

@@ -1,0 +1,143 @@
+"""Distribution tests of the native (Philox) random streams, through the C ABI:
+the Poisson sampler of wb200_counts / wb200_reads, the fp32 Box-Muller of the
+photon kernel and the fp64 normals of the per-pixel pass.  Stochastic-mode
+equivalence with the reference rests on these being the SAME distributions as
+np.random.poisson / np.random.normal / the reference's rand_r Box-Muller."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _poisson_draws(lam, n_samples=256, n_bins=4096, key=(7, 9)):
+    import torch
+    from wayne_b200 import _lib
+    dev = torch.device('cuda', 0)
+    f = torch.full((n_bins,), float(lam), dtype=torch.float64, device=dev)
+    one = torch.ones((n_bins,), dtype=torch.float64, device=dev)
+    dwl = torch.full((n_bins,), 1e-4, dtype=torch.float64, device=dev)     # x 1e4 -> 1
+    dur = torch.full((n_samples,), 1000.0, dtype=torch.float64, device=dev)  # x 1e-3 -> 1
+    counts = torch.empty((n_samples, n_bins), dtype=torch.int32, device=dev)
+    totals = torch.empty((n_samples,), dtype=torch.int64, device=dev)
+    _lib.check(_lib.lib.wb200_counts(n_samples, n_bins, _p(f), None, 0, _p(one), _p(dwl), _p(dur), 1.0,
+                                     _lib.COUNT_POISSON, key[0], key[1], None, _p(counts), _p(totals),
+                                     None), 'wb200_counts')
+    c = counts.cpu().numpy()
+    assert np.array_equal(c.sum(axis=1), totals.cpu().numpy())
+    return c.ravel()
+
+
+@pytest.mark.parametrize("lam", [0.05, 0.7, 3.0, 9.99, 10.0, 14.7, 60.0, 243.0, 4000.0, 2.5e5])
+def test_poisson_sampler_distribution(lam):
+    x = _poisson_draws(lam)
+    n = x.size
+    assert abs(x.mean() - lam) < 5 * np.sqrt(lam / n)
+    # var of the sample variance of a Poisson: (lam + 2 lam^2 (n/(n-1))) / n
+    assert abs(x.var() - lam) < 5 * np.sqrt((lam + 2 * lam * lam) / n)
+    # chi-square against the exact pmf on bins holding >= 50 expected draws
+    lo = int(max(0, np.floor(lam - 6 * np.sqrt(lam) - 2)))
+    hi = int(np.ceil(lam + 6 * np.sqrt(lam) + 3))
+    step = max(1, (hi - lo) // 200)
+    edges = np.arange(lo, hi + step, step)
+    obs = np.histogram(x, bins=np.append(edges, edges[-1] + step) - 0.5)[0][:-1]
+    cdf = stats.poisson.cdf(edges - 1, lam)
+    exp = np.diff(np.append(cdf, stats.poisson.cdf(edges[-1] + step - 1, lam)))[: len(obs)] * n
+    sel = exp >= 50
+    chi2 = ((obs[sel] - exp[sel]) ** 2 / exp[sel]).sum()
+    dof = sel.sum() - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+
+
+def test_poisson_independent_of_geometry_and_key():
+    a = _poisson_draws(37.0, 64, 1024, key=(1, 2))
+    b = _poisson_draws(37.0, 64, 1024, key=(1, 2))
+    c = _poisson_draws(37.0, 64, 1024, key=(1, 3))
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    # a sub-block of a bigger launch draws the same numbers (counter = (bin, sample))
+    big = _poisson_draws(37.0, 128, 1024, key=(1, 2)).reshape(128, 1024)
+    assert np.array_equal(big[:64].ravel(), a)
+
+
+def test_photon_normals_distribution():
+    """Marginal x / y distributions of electrons thrown from one bin: truncated
+    normal binned at integer pixels, chi-square against the exact cell
+    probabilities; narrow/wide mixture fractions respected."""
+    from wayne_b200 import pyparallel
+    n = 4_000_000
+    sig_l, sig_h, ratio = 9.0, 31.0, 0.25
+    x0, y0 = 512.3, 500.7
+    frame = pyparallel.psf_frame([n], [x0], [y0], [ratio], [sig_l], [sig_h], 1014, 1014, test=12345,
+                                 rng='philox')
+    assert frame.sum() > 0.999 * n
+    for axis, c0 in ((0, x0), (1, y0)):
+        obs = frame.sum(axis=axis).astype(float)
+        k = np.arange(1015)
+        cdf = ratio * stats.norm.cdf(k, c0, sig_h) + (1 - ratio) * stats.norm.cdf(k, c0, sig_l)
+        exp = np.diff(cdf) * n
+        sel = exp >= 100
+        chi2 = ((obs[sel] - exp[sel]) ** 2 / exp[sel]).sum()
+        dof = sel.sum() - 1
+        assert chi2 < dof + 6 * np.sqrt(2 * dof), (axis, chi2, dof)
+    # x and y of one electron are independent: correlation of the 2-D histogram ~ 0
+    yy, xx = np.mgrid[0:1014, 0:1014]
+    w = frame / frame.sum()
+    mx, my = (w * xx).sum(), (w * yy).sum()
+    cov = (w * (xx - mx) * (yy - my)).sum()
+    sx = np.sqrt((w * (xx - mx) ** 2).sum())
+    sy = np.sqrt((w * (yy - my) ** 2).sum())
+    assert abs(cov / (sx * sy)) < 5 / np.sqrt(n)
+
+
+def _reads_noise_only(read_noise=0.0, sky_rate=0.0, noise=(0.0, 0.0), F=266, R=3, key=(3, 4)):
+    import torch
+    from wayne_b200 import _lib
+    dev = torch.device('cuda', 0)
+    a = _lib.ReadsArgs()
+    a.n_reads, a.F, a.border = R, F, 5
+    a.add_read_noise = 1 if read_noise else 0
+    a.add_sky = 1 if sky_rate else 0
+    a.add_noise = 1 if noise[1] else 0
+    a.noise_mean, a.noise_std = noise
+    a.sky_rate, a.sky_f32 = sky_rate, 1
+    a.const_gain = 1.0
+    a.read_noise = read_noise
+    a.key0, a.key1 = key
+    dt = torch.tensor([1.0, 2.0, 4.0][:R], dtype=torch.float64, device=dev)
+    acc = torch.zeros((R, F, F), dtype=torch.float64, device=dev)
+    sky = torch.ones((F, F), dtype=torch.float64, device=dev)
+    out = torch.empty((R + 1, F, F), dtype=torch.float64, device=dev)
+    iters = torch.zeros((16,), dtype=torch.int32, device=dev)
+    a.d_dt, a.d_acc, a.d_sky, a.d_out = dt.data_ptr(), acc.data_ptr(), sky.data_ptr(), out.data_ptr()
+    a.d_newton_iters = iters.data_ptr()
+    _lib.check(_lib.lib.wb200_reads(C.byref(a), None), 'wb200_reads')
+    return out.cpu().numpy()
+
+
+def test_read_noise_normals():
+    out = _reads_noise_only(read_noise=6.0)
+    for r in range(4):
+        z = out[r] / 6.0
+        assert stats.kstest(z.ravel(), 'norm').pvalue > 1e-4
+        # the two pixels of a thread share one Philox call: still independent
+        assert abs(np.corrcoef(z[:, 0::2].ravel(), z[:, 1::2].ravel())[0, 1]) < 5 / np.sqrt(z.size / 2)
+    assert abs(np.corrcoef(out[0].ravel(), out[1].ravel())[0, 1]) < 0.02
+
+
+def test_sky_poisson_and_background_noise():
+    out = _reads_noise_only(sky_rate=14.7, noise=(0.5, 0.25))
+    inner = out[:, 5:-5, 5:-5]
+    d1 = inner[1]                       # first interval: Poisson(14.7 * 1) + N(0.5, 0.25)
+    n = d1.size
+    assert abs(d1.mean() - (14.7 + 0.5)) < 5 * np.sqrt((14.7 + 0.0625) / n)
+    assert abs(d1.var() - (14.7 + 0.0625)) < 0.35
+    d3 = inner[3] - inner[2]            # third interval, dt = 4
+    assert abs(d3.mean() - (14.7 * 4 + 2.0)) < 5 * np.sqrt((58.8 + 1.0) / n)
+    assert abs(d3.var() - (58.8 + 1.0)) < 1.5
+    assert np.all(out[:, :5, :] == 0) and np.all(out[:, :, -5:] == 0)   # reference pixels stay 0

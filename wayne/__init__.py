@@ -24,11 +24,19 @@ class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             return None
         return importlib.util.spec_from_loader(fullname, self)
 
+    _real_specs = {}
+
     def create_module(self, spec):
-        return importlib.import_module(_REAL + spec.name[len(__name__):])
+        mod = importlib.import_module(_REAL + spec.name[len(__name__):])
+        self._real_specs[spec.name] = mod.__spec__
+        return mod
 
     def exec_module(self, module):
-        pass
+        # the import machinery has just pointed __spec__ at the alias; the
+        # module keeps its own identity (relative imports inside it rely on it)
+        for alias, real in self._real_specs.items():
+            if real is not None and real.name == module.__name__:
+                module.__spec__ = real
 
 
 sys.meta_path.insert(0, _AliasFinder())

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -67,14 +68,35 @@ class DeviceEngine(object):
     def __init__(self, device):
         self.device = device
         self._planes = {}
+        self._pinned = {}
+        self._marks = []
+        self._open = {}
 
     # -- helpers -----------------------------------------------------------
     def stream_ptr(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def to_dev(self, a, dtype=None):
+        """Host array -> device tensor on the current stream (device tensors
+        pass through, so callers may keep large inputs resident in HBM)."""
+        if isinstance(a, torch.Tensor):
+            if a.device != self.device:
+                a = a.to(self.device, non_blocking=True)
+            return a if a.is_contiguous() else a.contiguous()
         a = np.ascontiguousarray(a, dtype=dtype)
         return torch.from_numpy(a).to(self.device, non_blocking=True)
+
+    def pinned_out(self, shape, dtype):
+        """A pinned host buffer for the exposure's device->host copy, as a numpy
+        array.  Buffers are pooled per (shape, dtype) and return to the pool when
+        the array (and every view of it) has been garbage collected, so the reads
+        an Exposure holds are never overwritten by a later exposure."""
+        key = (tuple(shape), dtype)
+        free = self._pinned.setdefault(key, [])
+        t = free.pop() if free else torch.empty(shape, dtype=dtype, pin_memory=True)
+        arr = t.numpy()
+        weakref.finalize(arr, free.append, t)
+        return t, arr
 
     def empty(self, shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -90,6 +112,14 @@ class DeviceEngine(object):
         out[BORDER:BORDER + n, BORDER:BORDER + n] = plane
         return out
 
+    def fetch(self, dev_tensor):
+        """Device tensor -> numpy array backed by pooled pinned memory; waits for
+        the stream, so everything queued before it has finished."""
+        t, arr = self.pinned_out(tuple(dev_tensor.shape), dev_tensor.dtype)
+        t.copy_(dev_tensor, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return arr
+
     def cached_plane(self, key, make):
         if key not in self._planes:
             self._planes[key] = make()
@@ -97,6 +127,32 @@ class DeviceEngine(object):
 
     def drop_planes(self):
         self._planes.clear()
+
+    # -- per-stage device timing (bench / profiles) ----------------------------
+    profile = False
+
+    def mark(self, name, begin):
+        """With ``profile`` on, bracket a stage with CUDA events on the current
+        stream (no synchronisation); read the totals with stage_times()."""
+        if not self.profile:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        if begin:
+            self._open[name] = ev
+        else:
+            self._marks.append((name, self._open.pop(name), ev))
+
+    def stage_times(self, reset=True):
+        """{stage: (total ms, launches)} of the marks recorded so far (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, a, b in self._marks:
+            t, n = out.get(name, (0.0, 0))
+            out[name] = (t + a.elapsed_time(b), n + 1)
+        if reset:
+            self._marks = []
+        return out
 
 
 class ExposureRun(object):
@@ -134,10 +190,13 @@ class ExposureRun(object):
         self.d_wl = e.to_dev(self.wl_host)
         self.d_flux = e.to_dev(flux, np.float64)
         if depth is not None:
-            depth = np.asarray(depth)
-            if depth.dtype != np.float64 or not depth.flags.c_contiguous:
-                depth = np.ascontiguousarray(depth, dtype=np.float64)
-            self.d_depth_full = torch.from_numpy(depth).to(e.device, non_blocking=True)
+            if not isinstance(depth, torch.Tensor):
+                depth = np.asarray(depth)
+                if depth.dtype != np.float64 or not depth.flags.c_contiguous:
+                    depth = np.ascontiguousarray(depth, dtype=np.float64)
+            elif depth.dtype != torch.float64:
+                raise ValueError("device planet_signal must be float64")
+            self.d_depth_full = e.to_dev(depth)
             self.depth_ld = int(depth.shape[1])
             self.depth_ptr = C.c_void_p(self.d_depth_full.data_ptr() + 8 * int(depth_col0))
         else:
@@ -210,12 +269,14 @@ class ExposureRun(object):
             self.d_counts = e.to_dev(c)
         else:
             self.d_counts = e.empty((self.N, self.W), torch.int32)
+        e.mark('k_counts', True)
         check(lib.wb200_counts(self.N, self.W, _ptr(self.d_flux), self.depth_ptr, self.depth_ld,
                                _ptr(self.d_sens), _ptr(self.d_dwl), _ptr(self.d_dur), self.scale,
                                mode, key[0] & 0xffffffff, key[1] & 0xffffffff,
                                _ptr(self.d_expected) if want_expected else None,
                                _ptr(self.d_counts), _ptr(self.d_totals), e.stream_ptr()),
               "wb200_counts")
+        e.mark('k_counts', False)
 
     def expected_host(self):
         if self.d_expected is None:
@@ -350,7 +411,9 @@ class ExposureRun(object):
             pa.d_win_ox = d_ox.data_ptr() + 4 * s0
             pa.d_win_oy = d_oy.data_ptr() + 4 * s0
             pa.d_lost = self.lost.data_ptr()
+            e.mark('k_throw', True)
             check(lib.wb200_throw_photons_at(C.byref(pa), s0, st), "wb200_throw_photons")
+            e.mark('k_throw', False)
 
             ga = _lib.GatherArgs()
             ga.n_samples, ga.sample0, ga.n_reads = n, s0, self.R
@@ -372,7 +435,9 @@ class ExposureRun(object):
             ga.d_win_oy = d_oy.data_ptr() + 4 * s0
             ga.d_trace = self.d_trace.data_ptr() + 8 * _lib.TRACE_STRIDE * s0
             ga.d_acc = self.d_acc.data_ptr()
+            e.mark('k_gather', True)
             check(lib.wb200_gather_flat(C.byref(ga), st), "wb200_gather_flat")
+            e.mark('k_gather', False)
         self._keep = (d_off, d_seeds, d_norm, d_nbase, d_ox, d_oy, d_win)
         return self.d_acc
 
@@ -462,7 +527,9 @@ class ExposureRun(object):
         a.d_newton_iters = d_iters.data_ptr()
         out = e.empty((R + 1, F, F), torch.float32 if out_f32 else torch.float64)
         a.d_out = out.data_ptr()
+        e.mark('k_reads', True)
         check(lib.wb200_reads(C.byref(a), st), "wb200_reads")
+        e.mark('k_reads', False)
         self._keep_reads = keep + [d_dt, d_iters]
         self.newton_iters = d_iters
         return out

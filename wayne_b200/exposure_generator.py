@@ -153,6 +153,11 @@ class ExposureGenerator(object):
             zero = zero + self.detector.get_initial_bias()
         return zero, {'cumulative_exp_time': 0 * u.s, 'read_exp_time': 0 * u.s, 'CRPIX1': 0}
 
+    @property
+    def photons(self):
+        """Electrons thrown by the last exposure (incl. those that left the frame)."""
+        return self._run.photons()
+
     # ------------------------------------------------------------------
     def _rng_mode(self):
         mode = self.rng if self.rng is not None else params.rng
@@ -160,10 +165,13 @@ class ExposureGenerator(object):
             raise ValueError("rng must be 'philox' or 'numpy', got {!r}".format(mode))
         return mode
 
-    def _default_key(self):
+    def _default_key(self, compat=False):
         seed = params.seed
         if seed is None:
-            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            # compat mode must not consume the numpy stream (its order is the
+            # reference's); native mode takes one draw so np.random.seed() still
+            # makes a run reproducible
+            seed = 0 if compat else int(np.random.randint(0, 2 ** 31 - 1))
         return (int(seed) & 0xffffffff, zlib.crc32(str(self.exp_info['filename']).encode()) & 0xffffffff)
 
     def _device_planes(self, eng, add_gain_variations, sky_background, add_non_linear, zero_read):
@@ -200,7 +208,7 @@ class ExposureGenerator(object):
                        add_gain_variations=True, add_non_linear=True, clip_values_det_limits=True,
                        add_read_noise=True, add_stellar_noise=True, add_initial_bias=True,
                        progress_bar=None, threads=2, rng_key=None, exact_newton=None,
-                       out_dtype=np.float64):
+                       out_dtype=np.float64, device_result=False):
         """Generate a spatially scanned exposure (see the module docstring).
 
         Units of bare numbers: ``wl`` micron, ``stellar_flux`` erg/(angstrom s
@@ -208,7 +216,10 @@ class ExposureGenerator(object):
         ``sky_background`` count/s.  Extra keywords over the reference:
         ``rng_key`` (Philox key pair), ``exact_newton`` (reference's global
         Newton stopping rule; default on in 'numpy' mode), ``out_dtype``
-        (float64 like the reference, or float32)."""
+        (float64 like the reference, or float32), ``device_result`` (leave the
+        reads in HBM as ``exposure.device_reads`` [NSAMP][F][F] and skip the
+        device->host copy; ``wl`` / ``stellar_flux`` stay host arrays but
+        ``planet_signal`` may be a CUDA tensor already resident in HBM)."""
         from . import _lib
         from .engine import DeviceEngine, ExposureRun
 
@@ -267,7 +278,7 @@ class ExposureGenerator(object):
         if len(dur_ms) < num_samples:      # bad SSV output: missing durations count as 0 (:340-342)
             dur_ms = np.concatenate([dur_ms, np.zeros(num_samples - len(dur_ms))])
         dt_s = np.diff(np.concatenate([[0.0], read_times_s]))
-        key = tuple(int(k) for k in (rng_key if rng_key is not None else self._default_key()))
+        key = tuple(int(k) for k in (rng_key if rng_key is not None else self._default_key(compat)))
 
         # ---- per-sub-sample seeds and pointing jitter (:327-329) ---------------
         if compat:
@@ -288,7 +299,7 @@ class ExposureGenerator(object):
         flux = np.asarray(getattr(stellar_flux, 'value', stellar_flux), dtype=np.float64)[i0:i1]
         depth = None
         if planet_signal is not None:
-            depth = np.asarray(planet_signal)
+            depth = planet_signal if hasattr(planet_signal, 'is_cuda') else np.asarray(planet_signal)
             if depth.ndim != 2 or depth.shape[0] < num_samples:
                 raise ValueError("planet_signal must be [n_samples][n_wl]")
             depth = depth[:num_samples]
@@ -385,9 +396,13 @@ class ExposureGenerator(object):
             exact_newton=bool(exact_newton and add_non_linear),
             out_f32=(np.dtype(out_dtype) == np.float32), const_gain=det.constant_gain)
 
-        reads_host = out.cpu().numpy()          # the single device -> host copy (synchronises)
+        if device_result:
+            self.exposure.device_reads = out
+            self.exp_info['sim_time'] = (time.time() - start_time) * u.s
+            return self.exposure
+        # the single device -> host copy, into pooled pinned memory (synchronises)
+        reads_host = eng.fetch(out)
         run.check_lost()
-        self.photons = run.photons()
 
         self.exposure.add_read(reads_host[0], zero_read_info)
         prev = 0.0

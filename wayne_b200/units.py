@@ -138,6 +138,11 @@ class Quantity(object):
     def __float__(self):
         return float(self.value)
 
+    def __bool__(self):
+        return bool(np.any(self.value))
+
+    __nonzero__ = __bool__
+
     def __repr__(self):
         return "<Quantity {} {}>".format(self.value, self.unit)
 
