@@ -280,6 +280,8 @@ class ExposureGenerator(object):
         dt_s = np.diff(np.concatenate([[0.0], read_times_s]))
         key = tuple(int(k) for k in (rng_key if rng_key is not None else self._default_key(compat)))
 
+        eng = DeviceEngine.get(self.device)
+
         # ---- per-sub-sample seeds and pointing jitter (:327-329) ---------------
         if compat:
             s_rand_seeds = np.random.randint(0, 100000, num_samples)
@@ -303,7 +305,6 @@ class ExposureGenerator(object):
             if depth.ndim != 2 or depth.shape[0] < num_samples:
                 raise ValueError("planet_signal must be [n_samples][n_wl]")
             depth = depth[:num_samples]
-        eng = DeviceEngine.get(self.device)
         run = ExposureRun(eng, self.grism, S, wl_um[i0:i1], flux, depth, i0,
                           x_ref + s_x_jitter, s_y_refs + s_y_jitter, dur_ms, scale_factor,
                           np.asarray(read_index, dtype=np.int32))
@@ -311,10 +312,17 @@ class ExposureGenerator(object):
 
         draws = {}
         cosmics = None
-        dark = None
+        dark = None          # host (dark, err) stacks: only the compat draws need them
+        d_dark = None        # resident device stacks (native mode)
         if add_dark:
             try:
-                dark = self._dark_stack(R)
+                if compat:
+                    dark = self._dark_stack(R)
+                else:
+                    def upload():
+                        host = self._dark_stack(R)
+                        return eng.to_dev(host[0]), eng.to_dev(host[1])
+                    d_dark = eng.cached_plane(('dark', S, self.SAMPSEQ, R), upload)
             except WFC3SimNoDarkFileError:
                 warnings.warn("No Dark file found for SAMPSEQ = {}, SUBARRAY={} - Switching Dark "
                               "Off".format(self.SAMPSEQ, S), WFC3SimNoDarkFileWarning)
@@ -384,10 +392,6 @@ class ExposureGenerator(object):
 
         sky_p, gain_p, nl_p, zero_p = self._device_planes(
             eng, add_gain_variations, sky_rate, add_non_linear, zero_read)
-        d_dark = None
-        if dark is not None:
-            d_dark = eng.cached_plane(('dark', S, self.SAMPSEQ, R),
-                                      lambda: (eng.to_dev(dark[0]), eng.to_dev(dark[1])))
         out = run.reads(
             dt_s, key=key, sky_rate=sky_rate, sky_plane=sky_p, gain_plane=gain_p, zero=zero_p,
             dark=d_dark, nl_planes=nl_p, noise=(noise_mean, noise_std) if use_noise else (0.0, 0.0),
