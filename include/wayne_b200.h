@@ -198,6 +198,10 @@ typedef struct wb200_gather_args {
                                 /* multiplies -- the reference stores it in    */
                                 /* np.ones_like(flat_f0), the FITS float32     */
                                 /* dtype (grism.py:380-385)                    */
+    int32_t exact;              /* 1: the reference's flat expression operation */
+                                /* for operation (fp64 divide + sqrt; parity   */
+                                /* mode); 0: hoisted reciprocals + FMAs (native)*/
+    int32_t pad0;
     double flat_wmin, flat_wmax;
     const int32_t *d_read_end;  /* [R] global index of each read's last sample */
     const int32_t *d_win;

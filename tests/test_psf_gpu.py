@@ -111,3 +111,38 @@ def test_philox_statistics(pyp):
     core = np.abs(rows - 121) <= 2
     fg, fr = gp[core.repeat(256, 1)].sum() / gp.sum(), cp[core.repeat(256, 1)].sum() / cp.sum()
     assert abs(fg - fr) < 2e-3
+
+
+def test_native_kernel_matches_generic_kernel(pyp, monkeypatch):
+    """The instruction-tuned Philox thrower draws the same electrons as the
+    generic kernel (same counters); approximate sqrt / magic-number floor may
+    move an electron across a pixel edge only at the 1e-5 level."""
+    case = O.psf_case(seed=21, n_bins=2048, mean_count=300.0)
+    args = (case["counts"], case["x"], case["y"], case["ratio"], case["sigl"], case["sigh"], 256, 256)
+    fast = pyp.psf_frame(*args, test=77, rng='philox')
+    monkeypatch.setenv("WB200_GENERIC_THROW", "1")
+    gen = pyp.psf_frame(*args, test=77, rng='philox')
+    assert fast.sum() == gen.sum() or abs(int(fast.sum()) - int(gen.sum())) <= 3
+    moved = np.abs(fast.astype(np.int64) - gen).sum() / 2
+    assert moved <= 2e-5 * gen.sum() + 2, moved
+
+
+def test_native_kernel_ragged_counts(pyp):
+    """Counts from 0 to thousands within one 32-bin group, odd counts, empty groups."""
+    rng = np.random.default_rng(8)
+    case = O.psf_case(seed=22, n_bins=1000, mean_count=1.0)
+    c = rng.integers(0, 4, 1000)
+    c[rng.integers(0, 1000, 30)] = rng.integers(500, 5000, 30)
+    c[200:330] = 0
+    c[999] = 1
+    case["counts"] = c.astype(np.int32)
+    args = (case["counts"], case["x"], case["y"], case["ratio"], case["sigl"], case["sigh"], 256, 256)
+    a = pyp.psf_frame(*args, test=5, rng='philox')
+    total = int(c.sum())
+    assert 0.99 * total < a.sum() <= total
+    # every bin's electrons are thrown: column profile follows the counts profile
+    prof = np.zeros(256)
+    np.add.at(prof, np.clip(case["x"].astype(int), 0, 255), c)
+    got = a.sum(axis=0).astype(float)
+    k = np.ones(25) / 25.0
+    assert np.abs(np.convolve(got, k, 'same') - np.convolve(prof, k, 'same')).max() < 0.08 * prof.max() + 50

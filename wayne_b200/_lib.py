@@ -50,7 +50,7 @@ class GatherArgs(C.Structure):
         ("L", c_i32), ("F", c_i32), ("border", c_i32),
         ("win_w", c_i32), ("win_h", c_i32),
         ("add_flat", c_i32), ("flat_off", c_i32), ("flat_n", c_i32),
-        ("flat_f32", c_i32),
+        ("flat_f32", c_i32), ("exact", c_i32), ("pad0", c_i32),
         ("flat_wmin", c_double), ("flat_wmax", c_double),
         ("d_read_end", c_void_p), ("d_win", c_void_p), ("d_win_ox", c_void_p),
         ("d_win_oy", c_void_p), ("d_trace", c_void_p),

@@ -10,6 +10,18 @@
 // accumulator -- the same sequence of fp64 operations per pixel as the
 // reference, so the interval planes are bit-reproducible (no float atomics).
 //
+// A CTA owns a 32 x 8 pixel rectangle of one read interval.  It first filters
+// the interval's sub-samples down to those whose window overlaps the rectangle
+// (one candidate per thread, ORDER-PRESERVING ballot compaction into shared
+// memory) and then loops over the survivors only: CTAs outside the scanned band
+// finish after the filter, CTAs inside it do no rejection work in the hot loop.
+//
+// EXACT = true   the reference's expression, operation for operation
+//                (fp64 divide + sqrt per evaluation): compat / parity mode.
+// EXACT = false  native mode: per-sample 1/sqrt(den) and 1/(wmax-wmin) hoisted,
+//                Horner FMAs -- same value to ~1e-15 relative before the float32
+//                rounding the reference applies to the flat value.
+//
 // Bound: HBM reads of the int32 windows (one coalesced row segment per
 // (CTA row, sub-sample) overlap) + one RMW of the fp64 interval plane.
 #pragma once
@@ -18,19 +30,19 @@
 
 namespace wb {
 
-constexpr int GX = 32, GY = 8;       // pixel tile of a CTA
-constexpr int G_SAMPLES = 128;       // sub-sample descriptors staged per pass
+constexpr int GX = 32, GY = 8;       // pixel rectangle of a CTA
+constexpr int G_THREADS = GX * GY;   // candidates filtered per pass
 
 struct GatherSample {
-    int ox, oy;
-    double x_ref, y_ref, a_t_i, den, m_w, c_w;
+    int ox, oy, s, pad;
+    double x_ref, y_ref, a_t_i, den, m_w, c_w; // den = a_t_i^2+1 (EXACT) or 1/sqrt(a_t_i^2+1)
 };
 
-// grism.py:359-385 for one pixel; X, Y are flat-plane indices (python-style
+// grism.py:359-385 for one pixel; Xd, Yd are flat-plane indices (python-style
 // negative wrap is applied by the caller before the plane lookups).
-__device__ __forceinline__ double flat_value(const GatherSample &g, double Xd, double Yd,
-                                             double f0, double f1, double f2, double f3,
-                                             double wmin, double wmax)
+__device__ __forceinline__ double flat_value_exact(const GatherSample &g, double Xd, double Yd,
+                                                   double f0, double f1, double f2, double f3,
+                                                   double wmin, double wmax)
 {
     const double arr = g.y_ref - Yd + g.a_t_i * g.x_ref - g.a_t_i * Xd;
     const double d = sqrt((arr * arr) / g.den);
@@ -41,13 +53,26 @@ __device__ __forceinline__ double flat_value(const GatherSample &g, double Xd, d
     return f0 + (f1 * n) + (f2 * n2) + (f3 * n3);
 }
 
-__global__ void __launch_bounds__(GX * GY) k_gather(const wb200_gather_args a)
+__device__ __forceinline__ double flat_value_fast(const GatherSample &g, double Xd, double Yd,
+                                                  double f0, double f1, double f2, double f3,
+                                                  double wmin, double inv_range)
 {
-    __shared__ GatherSample sm[G_SAMPLES];
+    const double arr = fma(g.a_t_i, g.x_ref - Xd, g.y_ref - Yd);
+    const double wl = fma(g.m_w, fabs(arr) * g.den, g.c_w);
+    const double n = (wl - wmin) * inv_range;
+    return fma(n, fma(n, fma(n, f3, f2), f1), f0);
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(G_THREADS) k_gather(const wb200_gather_args a)
+{
+    __shared__ GatherSample sm[G_THREADS];
+    __shared__ int s_wcount[G_THREADS / 32];
     const int r = blockIdx.z;
     const int c_l = blockIdx.x * GX + threadIdx.x; // light-sensitive coordinates
     const int r_l = blockIdx.y * GY + threadIdx.y;
     const int tid = threadIdx.y * GX + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const bool live = (c_l < a.L) && (r_l < a.L);
 
     // sub-samples of read interval r present in this window batch
@@ -61,9 +86,9 @@ __global__ void __launch_bounds__(GX * GY) k_gather(const wb200_gather_args a)
     // CTA pixel rectangle (light-sensitive coords == the frame coords of PSF())
     const int tx0 = blockIdx.x * GX, ty0 = blockIdx.y * GY;
 
-    size_t pix = ((size_t)r * a.F + (r_l + a.border)) * a.F + (c_l + a.border);
-    double acc = live ? a.d_acc[pix] : 0.0;
-    bool touched = false;
+    const size_t pix = ((size_t)r * a.F + (r_l + a.border)) * a.F + (c_l + a.border);
+    double acc = 0.0;
+    bool loaded = false, touched = false;
 
     // flat-plane indices of this pixel (grism.py:361-363), python negative wrap
     // (flat_xs/flat_ys are meshgrids looked up at the wrapped index, so the
@@ -78,37 +103,65 @@ __global__ void __launch_bounds__(GX * GY) k_gather(const wb200_gather_args a)
     const size_t fidx = (size_t)Yi * a.flat_n + Xi;
     double f0 = 1, f1 = 0, f2 = 0, f3 = 0;
     bool have_f = false;
+    const double inv_range = 1.0 / (a.flat_wmax - a.flat_wmin);
 
-    for (int base = lo; base < hi; base += G_SAMPLES) {
-        const int n = min(G_SAMPLES, hi - base);
+    for (int base = lo; base < hi; base += G_THREADS) {
+        // ---- filter: one candidate per thread, order-preserving compaction ----
+        const int s = base + tid;
+        int ox = 0, oy = 0;
+        bool sel = false;
+        if (s < hi) {
+            ox = a.d_win_ox[s];
+            oy = a.d_win_oy[s];
+            sel = !(ox >= tx0 + GX || ox + a.win_w <= tx0 || oy >= ty0 + GY || oy + a.win_h <= ty0);
+        }
+        const unsigned ballot = __ballot_sync(FULL, sel);
+        __syncthreads(); // previous pass's sm[] fully consumed
+        if (lane == 0)
+            s_wcount[warp] = __popc(ballot);
         __syncthreads();
-        for (int i = tid; i < n; i += GX * GY) {
-            const int s = base + i;
+        int pos = __popc(ballot & ((1u << lane) - 1u)), n = 0;
+#pragma unroll
+        for (int w = 0; w < G_THREADS / 32; ++w) {
+            const int c = s_wcount[w];
+            if (w < warp)
+                pos += c;
+            n += c;
+        }
+        if (n == 0)
+            continue; // uniform over the CTA
+        if (sel) {
             GatherSample g;
-            g.ox = a.d_win_ox[s];
-            g.oy = a.d_win_oy[s];
+            g.ox = ox;
+            g.oy = oy;
+            g.s = s;
+            g.pad = 0;
             const double *t = a.d_trace + (size_t)s * WB200_TRACE_STRIDE;
             g.x_ref = t[0];
             g.y_ref = t[1];
             g.a_t_i = 1 / t[2];
-            g.den = g.a_t_i * g.a_t_i + 1;
+            const double den = g.a_t_i * g.a_t_i + 1;
+            g.den = EXACT ? den : 1.0 / sqrt(den);
             g.m_w = t[4];
             g.c_w = t[5];
-            sm[i] = g;
+            sm[pos] = g;
         }
         __syncthreads();
+        if (!live)
+            continue;
+        // ---- hot loop: only windows that overlap this CTA's rectangle ----------
         for (int i = 0; i < n; ++i) {
             const GatherSample &g = sm[i];
-            // CTA-uniform rejection of windows that miss the pixel tile
-            if (g.ox >= tx0 + GX || g.ox + a.win_w <= tx0 || g.oy >= ty0 + GY ||
-                g.oy + a.win_h <= ty0)
-                continue;
             const int wx = c_l - g.ox, wy = r_l - g.oy;
-            if (!live || (unsigned)wx >= (unsigned)a.win_w || (unsigned)wy >= (unsigned)a.win_h)
+            if ((unsigned)wx >= (unsigned)a.win_w || (unsigned)wy >= (unsigned)a.win_h)
                 continue;
-            const int h = a.d_win[((size_t)(base + i) * a.win_h + wy) * a.win_w + wx];
+            const int h = a.d_win[((size_t)g.s * a.win_h + wy) * a.win_w + wx];
             if (h == 0)
                 continue;
+            if (!loaded) {
+                acc = a.d_acc[pix];
+                loaded = true;
+            }
             double v = (double)h;
             if (a.add_flat) {
                 if (!have_f && flat_ok) {
@@ -118,7 +171,8 @@ __global__ void __launch_bounds__(GX * GY) k_gather(const wb200_gather_args a)
                     f3 = a.d_flat[3][fidx];
                     have_f = true;
                 }
-                double fv = flat_value(g, Xd, Yd, f0, f1, f2, f3, a.flat_wmin, a.flat_wmax);
+                double fv = EXACT ? flat_value_exact(g, Xd, Yd, f0, f1, f2, f3, a.flat_wmin, a.flat_wmax)
+                                  : flat_value_fast(g, Xd, Yd, f0, f1, f2, f3, a.flat_wmin, inv_range);
                 if (a.flat_f32)
                     fv = (double)__double2float_rn(fv); // stored in ones_like(flat_f0)
                 v = v * fv;

@@ -335,4 +335,254 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Native (Philox) electron thrower, written for instruction count: the
+// baseline generic kernel above spends 111 warp-instructions per 32 electrons
+// (profiles/r01_k_throw_opcode_histogram_baseline.txt); most of them are the
+// per-unit shuffle binary search, the per-round Philox key bumps and the IEEE
+// sqrt / F2I sequences.  Here
+//   * a lane owns a contiguous RUN of units of its warp's 32-bin group: one
+//     binary search per lane and group, then a sequential walk that only steps
+//     to the next bin when its units are exhausted (bin parameters live in
+//     shared memory, 32 B per bin) -- no warp collectives in the hot loop;
+//   * the 20 Philox round keys are kernel parameters (constant-bank operands);
+//   * sqrt.approx / lg2.approx / sin.approx / cos.approx (4 MUFU per electron),
+//     floor by the round-down magic-number add (FADD.RM, no F2I on the XU pipe);
+//   * tile-relative unsigned bounds tests.
+// Same counters as the generic kernel -- (pair index, bin, sample, stream) -- so
+// a given key throws the same electrons whatever the launch geometry.
+// ---------------------------------------------------------------------------
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__device__ __forceinline__ uint4 philox4x32_10_keys(uint4 c, const PhiloxKeys &k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.k0[r], (uint32_t)p1,
+                       (uint32_t)(p0 >> 32) ^ c.w ^ k.k1[r], (uint32_t)p0);
+    }
+    return c;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// floor(v) for |v| < 2^22 without a conversion instruction: adding 1.5*2^23
+// with round-toward-minus-infinity leaves floor(v) in the low mantissa bits.
+__device__ __forceinline__ int floor_magic(float v)
+{
+    return __float_as_int(__fadd_rd(v, 12582912.0f)) - 0x4B400000;
+}
+
+struct BinPar {        // 32 bytes, two 128-bit shared loads
+    int excl, units, cnt, nh;
+    float fx, fy, sl, sh;
+};
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, const PhiloxKeys keys)
+{
+    const wb200_photon_args &a = p.a;
+    extern __shared__ int tile[]; // TH*TW
+    __shared__ float s_red[4][8];
+    __shared__ int s_org[2];
+    __shared__ __align__(16) BinPar s_bin[8][32];
+
+    const int s_local = blockIdx.y;
+    const uint32_t s_glob = (uint32_t)(p.sample0 + s_local);
+    const int W = a.n_bins;
+    const int w0 = blockIdx.x * a.chunk_bins;
+    const int w1 = min(W, w0 + a.chunk_bins);
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+
+    if (a.d_totals && a.d_totals[s_local] == 0)
+        return;
+
+    TraceCoef tc;
+    if (!a.d_xpos)
+        tc = load_trace(a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE);
+    const size_t row = (size_t)s_local * W;
+    auto bin_xy = [&](int w, double &x, double &y) {
+        if (a.d_xpos) {
+            x = a.d_xpos[row + w];
+            y = a.d_ypos[row + w];
+        } else {
+            trace_xy(tc, a.d_wl[w], a.sub_scale, x, y);
+        }
+    };
+
+    // ---- place the tile on the chunk's footprint (as in the generic kernel) ----
+    float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+    for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+        if (a.d_counts[row + w] <= 0)
+            continue;
+        double x, y;
+        bin_xy(w, x, y);
+        if (!(fabs(x) < 1e9) || !(fabs(y) < 1e9))
+            continue;
+        xmin = fminf(xmin, (float)x);
+        xmax = fmaxf(xmax, (float)x);
+        ymin = fminf(ymin, (float)y);
+        ymax = fmaxf(ymax, (float)y);
+    }
+    xmin = warp_min(xmin);
+    xmax = warp_max(xmax);
+    ymin = warp_min(ymin);
+    ymax = warp_max(ymax);
+    if (lane == 0) {
+        s_red[0][warp] = xmin;
+        s_red[1][warp] = xmax;
+        s_red[2][warp] = ymin;
+        s_red[3][warp] = ymax;
+    }
+    for (int i = threadIdx.x; i < TW * TH; i += blockDim.x)
+        tile[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < nwarps; ++i) {
+            xmin = fminf(xmin, s_red[0][i]);
+            xmax = fmaxf(xmax, s_red[1][i]);
+            ymin = fminf(ymin, s_red[2][i]);
+            ymax = fmaxf(ymax, s_red[3][i]);
+        }
+        int ox = 0, oy = 0;
+        if (xmin <= xmax) {
+            ox = (int)floorf(0.5f * (xmin + xmax)) - TW / 2;
+            oy = (int)floorf(0.5f * (ymin + ymax)) - TH / 2;
+        }
+        s_org[0] = ox;
+        s_org[1] = oy;
+    }
+    __syncthreads();
+    const int tx0 = s_org[0], ty0 = s_org[1];
+    // accepted tile-relative range [lo, lo+n): frame test 0 < x < nr, 0 < y < nc
+    const int lox = max(0, 1 - tx0), loy = max(0, 1 - ty0);
+    const unsigned nx = (unsigned)max(0, min(TW, a.nr - tx0) - lox);
+    const unsigned ny = (unsigned)max(0, min(TH, a.nc - ty0) - loy);
+    const int wox = a.d_win_ox[s_local], woy = a.d_win_oy[s_local];
+    BinPar *mybins = s_bin[warp];
+
+    const int ngroups = (w1 - w0 + 31) >> 5;
+    for (int g = warp; g < ngroups; g += nwarps) {
+        const int wb = w0 + (g << 5);
+        const int w = wb + lane;
+        BinPar bp;
+        bp.cnt = 0;
+        bp.nh = 0;
+        bp.fx = bp.fy = bp.sl = bp.sh = 0.f;
+        if (w < w1) {
+            const int cnt = a.d_counts[row + w];
+            if (cnt > 0) {
+                double bx, by;
+                bin_xy(w, bx, by);
+                bp.cnt = cnt;
+                // first N = (int)(counts*ratio) electrons take the wide Gaussian
+                // (pyparallel_menu.c:89-98)
+                bp.nh = __double2int_rz((double)cnt * a.d_ratio[w]);
+                bp.fx = (float)(bx - (double)tx0);
+                bp.fy = (float)(by - (double)ty0);
+                bp.sl = (float)a.d_sigl[w];
+                bp.sh = (float)a.d_sigh[w];
+                // bins that cannot reach the frame throw nothing: NaN / far-away
+                // positions, NaN widths (the reference's INT_MIN path), and widths
+                // beyond 1e5 px (keeps |coordinate| < 2^22 for floor_magic)
+                bool bad = !(fabsf(bp.fx) < 3.0e6f) || !(fabsf(bp.fy) < 3.0e6f);
+                if (bp.nh > 0 && !(fabsf(bp.sh) <= 1.0e5f))
+                    bad = true;
+                if (bp.cnt - bp.nh > 0 && !(fabsf(bp.sl) <= 1.0e5f))
+                    bad = true;
+                if (bad)
+                    bp.cnt = 0;
+            }
+        }
+        bp.units = (bp.cnt + 1) >> 1;
+        const int incl = warp_incl_scan(bp.units);
+        const int total = __shfl_sync(FULL, incl, 31);
+        bp.excl = incl - bp.units;
+        __syncwarp();
+        mybins[lane] = bp;
+        __syncwarp();
+        if (total == 0)
+            continue;
+        // this lane's run of units
+        const int K = (total + 31) >> 5;
+        int q = lane * K;
+        const int qend = min(q + K, total);
+        // first bin of the run: largest b with excl[b] <= q (all lanes search)
+        int b = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int v = __shfl_sync(FULL, incl, b + step - 1);
+            if (v <= q)
+                b += step;
+        }
+        if (q >= qend)
+            continue; // (no collectives below)
+        BinPar cur = mybins[b];
+        for (; q < qend; ++q) {
+            int j = q - cur.excl;
+            while (j >= cur.units) { // next bin with units (empty bins have units == 0)
+                ++b;
+                cur = mybins[b];
+                j = q - cur.excl;
+            }
+            const uint4 r = philox4x32_10_keys(
+                make_uint4((uint32_t)j, (uint32_t)(wb + b), s_glob, WB_STREAM_PHOTONS), keys);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 2 * j + h;
+                if (k >= cur.cnt)
+                    break;
+                const uint32_t ra = h ? r.z : r.x, rb = h ? r.w : r.y;
+                // Box-Muller: u1 in (0,1], theta in (-pi, pi)
+                const float u1 = fmaf((float)ra, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+                const float th = fmaf((float)rb, 1.4629180792671596e-09f, -3.14159265358979f);
+                const float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
+                const float sg = (k < cur.nh) ? cur.sh : cur.sl;
+                const float rs = rad * sg;
+                const int ix = floor_magic(fmaf(__cosf(th), rs, cur.fx));
+                const int iy = floor_magic(fmaf(__sinf(th), rs, cur.fy));
+                if ((unsigned)(ix - lox) < nx && (unsigned)(iy - loy) < ny) {
+                    atomicAdd(&tile[iy * TW + ix], 1);
+                } else {
+                    const int xa = ix + tx0, ya = iy + ty0;
+                    if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc)
+                        to_window(a, s_local, wox, woy, xa, ya);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- flush the tile into the sub-sample's HBM window ----------------------
+    for (int i = threadIdx.x; i < TW * TH; i += blockDim.x) {
+        const int v = tile[i];
+        if (v) {
+            const int iy = i / TW, ix = i - iy * TW;
+            const int wx = ix + tx0 - wox, wy = iy + ty0 - woy;
+            if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
+                atomicAdd(&a.d_win[((size_t)s_local * a.win_h + wy) * a.win_w + wx], v);
+            else
+                atomicAdd((unsigned long long *)a.d_lost, (unsigned long long)v);
+        }
+    }
+}
+
 } // namespace wb

@@ -75,8 +75,23 @@ static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t s
     p.a = *a;
     p.sample0 = sample0;
     switch (a->rng_mode) {
-    case WB200_RNG_PHILOX:
-        return launch_throw<WB200_RNG_PHILOX>(p, st);
+    case WB200_RNG_PHILOX: {
+        if (getenv("WB200_GENERIC_THROW"))      // A/B switch: the baseline generic kernel
+            return launch_throw<WB200_RNG_PHILOX>(p, st);
+        PhiloxKeys keys;
+        uint32_t k0 = a->key0, k1 = a->key1;
+        for (int r = 0; r < 10; ++r) {
+            keys.k0[r] = k0;
+            keys.k1[r] = k1;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        const int chunks = (a->n_bins + a->chunk_bins - 1) / a->chunk_bins;
+        dim3 grid(chunks, a->n_samples);
+        k_throw_philox<TILE_W, TILE_H><<<grid, 256, (size_t)TILE_W * TILE_H * sizeof(int), st>>>(p, keys);
+        WB_LAUNCHED("k_throw_philox");
+        return WB200_OK;
+    }
     case WB200_RNG_RANDR: {
         WB_REQUIRE(a->d_offsets && a->d_totals && a->d_seeds && a->threads >= 1, "RANDR inputs");
         int rc = ensure_lcg_tables();
@@ -228,7 +243,10 @@ int wb200_gather_flat(const wb200_gather_args *a, void *stream)
         return WB200_OK;
     dim3 grid((a->L + GX - 1) / GX, (a->L + GY - 1) / GY, a->n_reads);
     dim3 block(GX, GY);
-    k_gather<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+    if (a->exact)
+        k_gather<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+    else
+        k_gather<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
     WB_LAUNCHED("k_gather");
     return WB200_OK;
 }

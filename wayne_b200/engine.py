@@ -71,6 +71,9 @@ class DeviceEngine(object):
         self._pinned = {}
         self._marks = []
         self._open = {}
+        self._copy_stream = None
+        self._upload_stream = None
+        self._in_flight = []
 
     # -- helpers -----------------------------------------------------------
     def stream_ptr(self):
@@ -112,12 +115,58 @@ class DeviceEngine(object):
         out[BORDER:BORDER + n, BORDER:BORDER + n] = plane
         return out
 
+    MAX_IN_FLIGHT = 3      # device->host copies outstanding before the host waits
+
+    def _streams(self):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._upload_stream = torch.cuda.Stream(self.device)
+        return self._copy_stream, self._upload_stream
+
+    def upload_async(self, host_array):
+        """Large host array -> device on the upload stream; the current stream
+        waits for it, so the copy of exposure i+1 overlaps the kernels of i."""
+        _, up = self._streams()
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(up):
+            t = torch.from_numpy(host_array).to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(up)
+        cur.wait_event(ev)
+        t.record_stream(cur)
+        return t
+
+    def fetch_async(self, dev_tensor, small=None):
+        """Queue the device->host copy of ``dev_tensor`` (and of an optional small
+        tensor, e.g. a status word) on the copy stream behind everything already on
+        the current stream.  Returns (event, numpy array in pooled pinned memory,
+        small host tensor or None); both are valid once the event has completed."""
+        cs, _ = self._streams()
+        t, arr = self.pinned_out(tuple(dev_tensor.shape), dev_tensor.dtype)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        cs.wait_event(ready)
+        small_host = None
+        with torch.cuda.stream(cs):
+            t.copy_(dev_tensor, non_blocking=True)
+            if small is not None:
+                small_host = torch.empty(small.shape, dtype=small.dtype, pin_memory=True)
+                small_host.copy_(small, non_blocking=True)
+                small.record_stream(cs)
+        dev_tensor.record_stream(cs)
+        done = torch.cuda.Event()
+        done.record(cs)
+        self._in_flight.append(done)
+        while len(self._in_flight) > self.MAX_IN_FLIGHT:
+            self._in_flight.pop(0).synchronize()
+        return done, arr, small_host
+
     def fetch(self, dev_tensor):
         """Device tensor -> numpy array backed by pooled pinned memory; waits for
         the stream, so everything queued before it has finished."""
-        t, arr = self.pinned_out(tuple(dev_tensor.shape), dev_tensor.dtype)
-        t.copy_(dev_tensor, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        done, arr, _ = self.fetch_async(dev_tensor)
+        done.synchronize()
         return arr
 
     def cached_plane(self, key, make):
@@ -196,7 +245,8 @@ class ExposureRun(object):
                     depth = np.ascontiguousarray(depth, dtype=np.float64)
             elif depth.dtype != torch.float64:
                 raise ValueError("device planet_signal must be float64")
-            self.d_depth_full = e.to_dev(depth)
+            big = (not isinstance(depth, torch.Tensor)) and depth.nbytes >= (8 << 20)
+            self.d_depth_full = e.upload_async(depth) if big else e.to_dev(depth)
             self.depth_ld = int(depth.shape[1])
             self.depth_ptr = C.c_void_p(self.d_depth_full.data_ptr() + 8 * int(depth_col0))
         else:
@@ -420,6 +470,7 @@ class ExposureRun(object):
             ga.L, ga.F, ga.border = L, F, BORDER
             ga.win_w, ga.win_h = ww, wh
             ga.add_flat = 1 if add_flat else 0
+            ga.exact = 0 if rng_mode == _lib.RNG_PHILOX else 1
             ga.flat_off = g.flat_offset(self.S)
             if add_flat:
                 ga.flat_n = int(fl['f'][0].shape[0])

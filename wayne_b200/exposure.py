@@ -45,12 +45,30 @@ class Exposure(object):
         self.SUBARRAY = exp_info['SUBARRAY']
         self.NSAMP = exp_info['NSAMP']
         self.SAMPSEQ = exp_info['SAMPSEQ']
-        self.reads = []   # read 0 (zero read) first
+        self._reads = []   # read 0 (zero read) first
+        self._pending = None
 
     # -- container -------------------------------------------------------
+    @property
+    def reads(self):
+        """[(ndarray, header)], zero read first.  The device path hands the
+        exposure back while its device->host copy is still in flight; the first
+        access waits for it (so a driver that writes the FITS file right away
+        behaves exactly like the reference, and one that keeps generating
+        overlaps the copy with the next exposure)."""
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            pending(self)
+        return self._reads
+
+    @reads.setter
+    def reads(self, value):
+        self._pending = None
+        self._reads = value
+
     def add_read(self, data, read_info=None):
         header = self.generate_read_header(read_info) if read_info is not None else fits.Header()
-        self.reads.append((data, header))
+        self._reads.append((data, header))
 
     # -- host versions of the per-read operations --------------------------
     def _map(self, fn, start=0):

@@ -404,20 +404,30 @@ class ExposureGenerator(object):
             self.exposure.device_reads = out
             self.exp_info['sim_time'] = (time.time() - start_time) * u.s
             return self.exposure
-        # the single device -> host copy, into pooled pinned memory (synchronises)
-        reads_host = eng.fetch(out)
-        run.check_lost()
+        # the single device -> host copy, queued on the copy stream into pooled
+        # pinned memory; exposure.reads waits for it on first access
+        done, reads_host, lost = eng.fetch_async(out, small=run.lost)
+        nsamp = self.NSAMP
 
-        self.exposure.add_read(reads_host[0], zero_read_info)
-        prev = 0.0
-        for r in range(R):
-            self.exposure.add_read(reads_host[r + 1], {
-                'cumulative_exp_time': read_times_s[r] * u.s,
-                'read_exp_time': (read_times_s[r] - prev) * u.s,
-                'CRPIX1': 0,
-            })
-            prev = read_times_s[r]
-        assert len(self.exposure.reads) == self.NSAMP
+        def materialize(exp):
+            done.synchronize()
+            n_lost = int(lost[0])
+            if n_lost:
+                raise _lib.WayneB200Error(
+                    "{} electrons fell outside their sub-sample window".format(n_lost))
+            exp.add_read(reads_host[0], zero_read_info)
+            prev = 0.0
+            for r in range(R):
+                exp.add_read(reads_host[r + 1], {
+                    'cumulative_exp_time': read_times_s[r] * u.s,
+                    'read_exp_time': (read_times_s[r] - prev) * u.s,
+                    'CRPIX1': 0,
+                })
+                prev = read_times_s[r]
+            assert len(exp._reads) == nsamp
+            exp.exp_info['sim_time'] = (time.time() - start_time) * u.s
+
+        self.exposure._pending = materialize
 
         if progress_bar is not None:
             progress_bar.print_status_line(
