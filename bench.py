@@ -110,42 +110,52 @@ def frame_kwargs(wk, i):
 
 
 class ClockSampler(object):
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region.
 
-    def __init__(self, index):
-        self.p = None
+    In-process NVML (nvidia_ml_py) from a thread: spawning `nvidia-smi -lms` next
+    to the bench stalls the CUDA driver for 50-100 ms at a time on this box (seen
+    as host-issue outliers), a lightweight NVML query every 25 ms does not."""
+
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20),
+               ('sw_power_cap', 0x4))
+
+    def __init__(self, index, period=0.025):
+        import threading
+        self.samples, self.mask, self.max_mhz, self.err = [], 0, None, None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
-                                       '--format=csv,noheader,nounits', '-lms', '20'],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:          # noqa: BLE001
+            self.err = 'nvml unavailable: %s' % exc
+            return
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:         # noqa: BLE001
+                    pass
+                self._stop.wait(period)
+
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.p is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.p.terminate()
-        out = self.p.communicate()[0]
-        sm, mx, reasons = [], [], set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(',')]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': float(max(mx)) if mx else None, 'samples': len(sm),
-                'reasons': sorted(reasons)}
+        if self.err:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [self.err]}
+        self._stop.set()
+        self.t.join()
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'samples': len(self.samples),
+                'reasons': [n for n, bit in self.REASONS if self.mask & bit],
+                'source': 'NVML, in-process, every 25 ms during the timed region'}
 
 
 def measured_peaks():
@@ -302,7 +312,7 @@ def run_native(args, wk):
     for i in range(args.warmup):
         one(i, True)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('WB200_NO_CLOCKS')) else None
     eng.profile = True
     eng.stage_times()
     l0 = _lib.launch_count()
@@ -312,8 +322,11 @@ def run_native(args, wk):
     phot_acc = torch.zeros((), dtype=torch.int64, device=dev)
     lost_acc = torch.zeros((1,), dtype=torch.int64, device=dev)
     geom = None
+    v_issue = []
     for i in range(args.steps):
+        ta = time.perf_counter()
         eg, _ = one(args.warmup + i, True)
+        v_issue.append((time.perf_counter() - ta) * 1e3)
         phot_acc += eg._run.d_totals.sum()       # device-side bookkeeping, no sync
         lost_acc += eg._run.lost
         geom = eg._run.win_geometry
@@ -331,20 +344,27 @@ def run_native(args, wk):
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside ---------------
     import collections
-    for i in range(max(1, args.warmup // 2)):
-        one(i, False)[1].reads
+    warm = [one(i, False)[1] for i in range(max(6, args.warmup))]   # fills the pinned-buffer pool
+    for w_ in warm:
+        w_.reads
+    del warm
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     pending = collections.deque()
     checksum = 0.0
+    t_issue, t_wait = [], []
     for i in range(args.steps):
+        ta = time.perf_counter()
         _, exp = one(args.warmup + i, False)
+        tb = time.perf_counter()
         pending.append(exp)
         while len(pending) > 2:              # the consumer: read every exposure's result on the host
             reads = pending.popleft().reads
             d2h = sum(r[0].nbytes for r in reads)
             checksum += float(reads[-1][0][512 % reads[-1][0].shape[0], 7])
+        t_issue.append((tb - ta) * 1e3)
+        t_wait.append((time.perf_counter() - tb) * 1e3)
     while pending:
         reads = pending.popleft().reads
         d2h = sum(r[0].nbytes for r in reads)
@@ -404,8 +424,11 @@ def run_native(args, wk):
                    'l2': 'no flush: per-exposure working set (windows+planes+reads, > 500 MB) exceeds the 126 MB L2'},
         'clocks': clocks,
         'e2e': {'value': world * 1e3 / ms_e2e, 'unit': 'exposures/s', 'ms_per_step': ms_e2e,
-                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'host_issue_ms': [round(float(np.median(t_issue)), 3), round(float(np.max(t_issue)), 3)],
+                'host_wait_ms': [round(float(np.median(t_wait)), 3), round(float(np.max(t_wait)), 3)]},
         'gpu_launches': int(launches),
+        'host_issue_ms': [round(float(np.median(v_issue)), 3), round(float(np.max(v_issue)), 3)],
         'stage_ms': {k: v[0] / args.steps for k, v in stages.items()},
         'dominant_kernel': dominant,
         'roofline': roof_throw if dominant == 'k_throw' else roof_hbm,

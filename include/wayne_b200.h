@@ -237,7 +237,9 @@ typedef struct wb200_reads_args {
     double noise_mean, noise_std;   /* per second (exposure_generator.py:477-479) */
     double sky_rate;            /* counts/s                                     */
     int32_t sky_f32;            /* 1: Poisson mean = float32(sky)*float32(rate*dt), */
-    int32_t pad0;               /* the in-place float32 product of :489-493     */
+                                /* the in-place float32 product of :489-493     */
+    int32_t fast_math;          /* 1 (native mode): fp32-SFU normals, reciprocal */
+                                /* gain; 0: fp64 expressions of the reference    */
     double const_gain;          /* 2.35, used when d_gain == NULL               */
     double clip_lo, clip_hi;    /* -20, 78000                                   */
     double read_noise;          /* 14.1/2.35                                    */

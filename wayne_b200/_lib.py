@@ -67,7 +67,7 @@ class ReadsArgs(C.Structure):
         ("exact_newton", c_i32), ("n_cosmics", c_i32),
         ("key0", c_u32), ("key1", c_u32),
         ("noise_mean", c_double), ("noise_std", c_double), ("sky_rate", c_double),
-        ("sky_f32", c_i32), ("pad0", c_i32),
+        ("sky_f32", c_i32), ("fast_math", c_i32),
         ("const_gain", c_double), ("clip_lo", c_double), ("clip_hi", c_double),
         ("read_noise", c_double),
         ("d_dt", c_void_p), ("d_acc", c_void_p), ("d_sky", c_void_p), ("d_gain", c_void_p),

@@ -372,14 +372,32 @@ __device__ __forceinline__ uint4 philox4x32_10_keys(uint4 c, const PhiloxKeys &k
 __device__ __forceinline__ float sqrt_approx(float x)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// u1 >= 2^-33 is never denormal, so the flush-to-zero forms are exact here and
+// save the denormal pre-scaling the non-ftz forms expand to
 __device__ __forceinline__ float lg2_approx(float x)
 {
     float r;
-    asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+__device__ __forceinline__ float sin_approx(float x)
+{
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float cos_approx(float x)
+{
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void red_shared_inc(uint32_t addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
 // floor(v) for |v| < 2^22 without a conversion instruction: adding 1.5*2^23
@@ -478,6 +496,11 @@ __global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, cons
     const unsigned ny = (unsigned)max(0, min(TH, a.nc - ty0) - loy);
     const int wox = a.d_win_ox[s_local], woy = a.d_win_oy[s_local];
     BinPar *mybins = s_bin[warp];
+    // bin positions are staged relative to the ACCEPTED origin (tx0+lox, ty0+loy),
+    // so one unsigned compare per axis is the whole bounds test, and the tile cell
+    // of accepted (ix, iy) is tile_acc + (iy*TW + ix)*4 in the shared window
+    const int ax0 = tx0 + lox, ay0 = ty0 + loy;
+    const uint32_t tile_acc = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)((loy * TW + lox) * 4);
 
     const int ngroups = (w1 - w0 + 31) >> 5;
     for (int g = warp; g < ngroups; g += nwarps) {
@@ -496,8 +519,8 @@ __global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, cons
                 // first N = (int)(counts*ratio) electrons take the wide Gaussian
                 // (pyparallel_menu.c:89-98)
                 bp.nh = __double2int_rz((double)cnt * a.d_ratio[w]);
-                bp.fx = (float)(bx - (double)tx0);
-                bp.fy = (float)(by - (double)ty0);
+                bp.fx = (float)(bx - (double)ax0);
+                bp.fy = (float)(by - (double)ay0);
                 bp.sl = (float)a.d_sigl[w];
                 bp.sh = (float)a.d_sigh[w];
                 // bins that cannot reach the frame throw nothing: NaN / far-away
@@ -557,12 +580,12 @@ __global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, cons
                 const float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
                 const float sg = (k < cur.nh) ? cur.sh : cur.sl;
                 const float rs = rad * sg;
-                const int ix = floor_magic(fmaf(__cosf(th), rs, cur.fx));
-                const int iy = floor_magic(fmaf(__sinf(th), rs, cur.fy));
-                if ((unsigned)(ix - lox) < nx && (unsigned)(iy - loy) < ny) {
-                    atomicAdd(&tile[iy * TW + ix], 1);
+                const int ix = floor_magic(fmaf(cos_approx(th), rs, cur.fx));
+                const int iy = floor_magic(fmaf(sin_approx(th), rs, cur.fy));
+                if ((unsigned)ix < nx && (unsigned)iy < ny) {
+                    red_shared_inc(tile_acc + (uint32_t)(iy * (TW * 4) + ix * 4));
                 } else {
-                    const int xa = ix + tx0, ya = iy + ty0;
+                    const int xa = ix + ax0, ya = iy + ay0;
                     if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc)
                         to_window(a, s_local, wox, woy, xa, ya);
                 }

@@ -77,7 +77,9 @@ __device__ __forceinline__ void load_pair(const double *plane, size_t i, double 
 //         (the reference stops all pixels together, detector.py:344).
 // PASS 2: exact mode, second half -- applies exactly that many steps to every
 //         pixel, then clip / border / zero read / read noise.
-template <int PASS>
+// FAST (native mode only): fp32-SFU Box-Muller for the noise normals and a
+// reciprocal gain -- distributions unchanged, values not bit-tied to numpy.
+template <int PASS, bool FAST = false>
 __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
 {
     const int F = a.F, B = a.border, R = a.n_reads;
@@ -125,6 +127,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
         }
     }
 
+    if (FAST) {
+        gain[0] = 1.0 / gain[0];
+        gain[1] = 1.0 / gain[1];
+    }
     // zero read as it is after clip + reference-pixel reset (exposure.py:82-131)
     double zc[2];
     for (int h = 0; h < 2; ++h) {
@@ -161,7 +167,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                                 const uint4 q = philox4x32_10(
                                     make_uint4(0, pid, (uint32_t)r, WB_STREAM_NOISE), a.key0, a.key1);
                                 double z0, z1;
-                                box_muller_d(q.x, q.y, z0, z1);
+                                if (FAST)
+                                    box_muller_fd(q.x, q.y, z0, z1);
+                                else
+                                    box_muller_d(q.x, q.y, z0, z1);
                                 px = px + (a.noise_mean * dt + (a.noise_std * dt) * z0);
                             }
                         }
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                                     e += a.d_cos_energy[c];
                             px = px + e;
                         }
-                        px = px / gain[h];
+                        px = FAST ? px * gain[h] : px / gain[h];
                     }
                     cum[h] = cum[h] + px;
                     v[h] = cum[h];
@@ -202,7 +211,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                         const uint4 q = philox4x32_10(
                             make_uint4(0, (uint32_t)p, (uint32_t)r, WB_STREAM_DARK), a.key0, a.key1);
                         double z[2];
-                        box_muller_d(q.x, q.y, z[0], z[1]);
+                        if (FAST)
+                            box_muller_fd(q.x, q.y, z[0], z[1]);
+                        else
+                            box_muller_d(q.x, q.y, z[0], z[1]);
                         for (int h = 0; h < 2; ++h) {
                             const double sd = (de[h] > 0) ? de[h] : 0.00001; // detector.py:189-190
                             v[h] = v[h] + (dk[h] + sd * z[h]);
@@ -255,7 +267,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
             } else {
                 const uint4 q = philox4x32_10(
                     make_uint4(0, (uint32_t)p, (uint32_t)(r + 1), WB_STREAM_READ), a.key0, a.key1);
-                box_muller_d(q.x, q.y, z[0], z[1]);
+                if (FAST)
+                    box_muller_fd(q.x, q.y, z[0], z[1]);
+                else
+                    box_muller_d(q.x, q.y, z[0], z[1]);
             }
             v[0] = v[0] + a.read_noise * z[0]; // detector.py:198
             v[1] = v[1] + a.read_noise * z[1];
@@ -285,7 +300,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
         } else {
             const uint4 q =
                 philox4x32_10(make_uint4(0, (uint32_t)p, 0u, WB_STREAM_READ), a.key0, a.key1);
-            box_muller_d(q.x, q.y, z[0], z[1]);
+            if (FAST)
+                box_muller_fd(q.x, q.y, z[0], z[1]);
+            else
+                box_muller_d(q.x, q.y, z[0], z[1]);
         }
         v[0] = v[0] + a.read_noise * z[0];
         v[1] = v[1] + a.read_noise * z[1];

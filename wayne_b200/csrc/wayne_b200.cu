@@ -290,7 +290,10 @@ int wb200_reads(const wb200_reads_args *a, void *stream)
         k_reads<2><<<blocks, 256, 0, st>>>(*a);
         WB_LAUNCHED("k_reads<2>");
     } else {
-        k_reads<0><<<blocks, 256, 0, st>>>(*a);
+        if (a->fast_math && !getenv("WB200_EXACT_READS"))
+            k_reads<0, true><<<blocks, 256, 0, st>>>(*a);
+        else
+            k_reads<0, false><<<blocks, 256, 0, st>>>(*a);
         WB_LAUNCHED("k_reads<0>");
     }
     return WB200_OK;

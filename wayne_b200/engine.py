@@ -506,7 +506,7 @@ class ExposureRun(object):
     def reads(self, dt_s, key=(0, 0), sky_rate=0.0, sky_plane=None, gain_plane=None, zero=None,
               dark=None, nl_planes=None, noise=(0.0, 0.0), clip=None, read_noise=0.0,
               cosmics=None, draws=None, exact_newton=False, out_f32=False, const_gain=2.35,
-              sky_f32=True):
+              sky_f32=True, fast_math=False):
         """Stage 4.  Planes are device tensors [F][F] (bordered) or None.
 
         dark = (dark[R][F][F], err[R][F][F]) device tensors; cosmics =
@@ -530,6 +530,7 @@ class ExposureRun(object):
         a.noise_mean, a.noise_std = float(noise[0] or 0.0), float(noise[1] or 0.0)
         a.sky_rate = float(sky_rate or 0.0)
         a.sky_f32 = 1 if sky_f32 else 0
+        a.fast_math = 1 if fast_math else 0
         a.const_gain = float(const_gain)
         a.clip_lo, a.clip_hi = (float(clip[0]), float(clip[1])) if clip is not None else (0.0, 0.0)
         a.read_noise = float(read_noise or 0.0)

@@ -398,7 +398,8 @@ class ExposureGenerator(object):
             clip=(det.min_counts, det.max_counts) if clip_values_det_limits else None,
             read_noise=det.read_noise if add_read_noise else 0.0, cosmics=cosmics, draws=draws,
             exact_newton=bool(exact_newton and add_non_linear),
-            out_f32=(np.dtype(out_dtype) == np.float32), const_gain=det.constant_gain)
+            out_f32=(np.dtype(out_dtype) == np.float32), const_gain=det.constant_gain,
+            fast_math=not compat)
 
         if device_result:
             self.exposure.device_reads = out
