@@ -316,6 +316,7 @@ def run_native(args, wk):
     # (the NVML sampler thread is started before the warm-up so its start-up cost
     # is outside the timed region; its samples are reset when the clock starts)
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('WB200_NO_CLOCKS')) else None
+    eng.profile = True               # stage events on in the warm-up too (first-use costs)
     for i in range(args.warmup):
         one(i, True)
     barrier()

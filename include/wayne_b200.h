@@ -214,6 +214,16 @@ typedef struct wb200_gather_args {
 
 int wb200_gather_flat(const wb200_gather_args *args, void *stream);
 
+/* Native mode, stages 2+3+3b in ONE launch: throw (Philox), bin in shared-memory
+ * tiles, and at tile flush apply the sub-sample's flat and add count*flat into
+ * the read interval's plane -- no per-sub-sample HBM windows, no gather pass.
+ * `g` supplies geometry, flat planes, d_read_end, d_trace (win_* fields unused);
+ * g->d_acc is [n_reads][F][F] INT64 fixed point, 2^24 per electron (integer
+ * atomics commute: bit-reproducible), zeroed by the caller; wb200_reads reads it
+ * with acc_fixed = 1.  args->d_win* / d_lost are unused. */
+int wb200_throw_photons_direct(const wb200_photon_args *args, const wb200_gather_args *g,
+                               int sample0, void *stream);
+
 /* --------------------------------------------------------------------------
  * Stage 4: the fused per-pixel pass over all reads.  Replaces
  * _add_read_reductions (wayne/exposure_generator.py:468-515), the cumulative
@@ -240,11 +250,14 @@ typedef struct wb200_reads_args {
                                 /* the in-place float32 product of :489-493     */
     int32_t fast_math;          /* 1 (native mode): fp32-SFU normals, reciprocal */
                                 /* gain; 0: fp64 expressions of the reference    */
+    int32_t acc_fixed;          /* 1: d_acc is int64 fixed point (2^24 / electron) */
+    int32_t pad1;
     double const_gain;          /* 2.35, used when d_gain == NULL               */
     double clip_lo, clip_hi;    /* -20, 78000                                   */
     double read_noise;          /* 14.1/2.35                                    */
     const double *d_dt;         /* [R] read interval lengths, seconds           */
-    const double *d_acc;        /* [R][F][F] electrons per interval             */
+    const void *d_acc;          /* [R][F][F] electrons per interval: float64, or */
+                                /* int64 fixed point when acc_fixed             */
     const double *d_sky;        /* master sky plane                             */
     const double *d_gain;       /* 2.35/pfl plane or NULL                       */
     const double *d_zero;       /* zero read (initial bias) or NULL (= zeros)   */

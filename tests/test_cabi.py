@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     from wayne_b200 import _lib
     assert ctypes.sizeof(_lib.PhotonArgs) == 9 * 4 + 4 + 8 + 8 + 17 * 8
     assert ctypes.sizeof(_lib.GatherArgs) == 14 * 4 + 2 * 8 + 5 * 8 + 4 * 8 + 8
-    assert ctypes.sizeof(_lib.ReadsArgs) == 12 * 4 + 8 + 3 * 8 + 8 + 4 * 8 + 7 * 8 + 7 * 8 + 4 * 8 + 4 * 8 + 2 * 8
+    assert ctypes.sizeof(_lib.ReadsArgs) == 12 * 4 + 8 + 3 * 8 + 8 + 8 + 4 * 8 + 7 * 8 + 7 * 8 + 4 * 8 + 4 * 8 + 2 * 8
 
 
 def test_no_oracle_import_in_product():

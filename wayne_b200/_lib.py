@@ -67,7 +67,7 @@ class ReadsArgs(C.Structure):
         ("exact_newton", c_i32), ("n_cosmics", c_i32),
         ("key0", c_u32), ("key1", c_u32),
         ("noise_mean", c_double), ("noise_std", c_double), ("sky_rate", c_double),
-        ("sky_f32", c_i32), ("fast_math", c_i32),
+        ("sky_f32", c_i32), ("fast_math", c_i32), ("acc_fixed", c_i32), ("pad1", c_i32),
         ("const_gain", c_double), ("clip_lo", c_double), ("clip_hi", c_double),
         ("read_noise", c_double),
         ("d_dt", c_void_p), ("d_acc", c_void_p), ("d_sky", c_void_p), ("d_gain", c_void_p),
@@ -103,6 +103,7 @@ SIGNATURES = {
     "wb200_throw_photons": (c_int, [C.POINTER(PhotonArgs), c_void_p]),
     "wb200_throw_photons_at": (c_int, [C.POINTER(PhotonArgs), c_int, c_void_p]),
     "wb200_gather_flat": (c_int, [C.POINTER(GatherArgs), c_void_p]),
+    "wb200_throw_photons_direct": (c_int, [C.POINTER(PhotonArgs), C.POINTER(GatherArgs), c_int, c_void_p]),
     "wb200_reads": (c_int, [C.POINTER(ReadsArgs), c_void_p]),
     "wb200_cosmic_chains": (c_int, [c_int, c_void_p, c_i32, c_void_p, c_void_p, c_void_p]),
     "wb200_microbench": (c_int, [c_int, c_int, DP, DP]),

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "stage1.cuh"
+#include "gather.cuh"
 
 namespace wb {
 
@@ -412,8 +413,49 @@ struct BinPar {        // 32 bytes, two 128-bit shared loads
     float fx, fy, sl, sh;
 };
 
-template <int TW, int TH>
-__global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, const PhiloxKeys keys)
+// DIRECT = false: tiles are flushed (integer red) into the per-sub-sample HBM
+//                  windows and k_gather applies the flat afterwards.
+// DIRECT = true : no windows and no gather pass.  At flush each non-zero tile
+//                  cell evaluates ITS sub-sample's flat once (grism.py:359-385,
+//                  fast form) and adds count*flat to the read interval's plane
+//                  as a 2^-24 fixed-point 64-bit integer: integer atomics
+//                  commute, so the planes stay bit-reproducible whatever the
+//                  launch geometry, and HBM never sees a per-sub-sample buffer.
+constexpr double WB_ACC_SCALE = 16777216.0; // 2^24 per electron
+
+struct DirectSample {
+    GatherSample g;
+    long long *acc; // plane of this sub-sample's read interval
+    double inv_range;
+};
+
+__device__ __forceinline__ void deposit(const wb200_gather_args &ga, const DirectSample &d, int xa,
+                                        int ya, int count)
+{
+    double v = (double)count;
+    if (ga.add_flat) {
+        int Xi = xa + ga.flat_off, Yi = ya + ga.flat_off;
+        if (Xi < 0)
+            Xi += ga.flat_n;
+        if (Yi < 0)
+            Yi += ga.flat_n;
+        if ((unsigned)Xi < (unsigned)ga.flat_n && (unsigned)Yi < (unsigned)ga.flat_n) {
+            const size_t fi = (size_t)Yi * ga.flat_n + Xi;
+            double fv = flat_value_fast(d.g, (double)Xi, (double)Yi, ga.d_flat[0][fi], ga.d_flat[1][fi],
+                                        ga.d_flat[2][fi], ga.d_flat[3][fi], ga.flat_wmin, d.inv_range);
+            if (ga.flat_f32)
+                fv = (double)__double2float_rn(fv);
+            v *= fv;
+        }
+    }
+    const long long q = __double2ll_rn(v * WB_ACC_SCALE);
+    atomicAdd((unsigned long long *)(d.acc + (size_t)(ya + ga.border) * ga.F + (xa + ga.border)),
+              (unsigned long long)q);
+}
+
+template <int TW, int TH, bool DIRECT>
+__global__ void __launch_bounds__(256)
+k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_args ga)
 {
     const wb200_photon_args &a = p.a;
     extern __shared__ int tile[]; // TH*TW
@@ -494,7 +536,26 @@ __global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, cons
     const int lox = max(0, 1 - tx0), loy = max(0, 1 - ty0);
     const unsigned nx = (unsigned)max(0, min(TW, a.nr - tx0) - lox);
     const unsigned ny = (unsigned)max(0, min(TH, a.nc - ty0) - loy);
-    const int wox = a.d_win_ox[s_local], woy = a.d_win_oy[s_local];
+    int wox = 0, woy = 0;
+    DirectSample ds;
+    if (DIRECT) {
+        const double *t = a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE;
+        ds.g.ox = ds.g.oy = ds.g.s = ds.g.pad = 0;
+        ds.g.x_ref = t[0];
+        ds.g.y_ref = t[1];
+        ds.g.a_t_i = 1 / t[2];
+        ds.g.den = 1.0 / sqrt(ds.g.a_t_i * ds.g.a_t_i + 1);
+        ds.g.m_w = t[4];
+        ds.g.c_w = t[5];
+        ds.inv_range = 1.0 / (ga.flat_wmax - ga.flat_wmin);
+        int r = 0; // read interval of this sub-sample: first r with read_end[r] >= s
+        while (r + 1 < ga.n_reads && ga.d_read_end[r] < (int)s_glob)
+            ++r;
+        ds.acc = reinterpret_cast<long long *>(ga.d_acc) + (size_t)r * ga.F * ga.F;
+    } else {
+        wox = a.d_win_ox[s_local];
+        woy = a.d_win_oy[s_local];
+    }
     BinPar *mybins = s_bin[warp];
     // bin positions are staged relative to the ACCEPTED origin (tx0+lox, ty0+loy),
     // so one unsigned compare per axis is the whole bounds test, and the tile cell
@@ -586,24 +647,32 @@ __global__ void __launch_bounds__(256) k_throw_philox(const PhotonParams p, cons
                     red_shared_inc(tile_acc + (uint32_t)(iy * (TW * 4) + ix * 4));
                 } else {
                     const int xa = ix + ax0, ya = iy + ay0;
-                    if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc)
-                        to_window(a, s_local, wox, woy, xa, ya);
+                    if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
+                        if (DIRECT)
+                            deposit(ga, ds, xa, ya, 1);
+                        else
+                            to_window(a, s_local, wox, woy, xa, ya);
+                    }
                 }
             }
         }
     }
     __syncthreads();
 
-    // ---- flush the tile into the sub-sample's HBM window ----------------------
+    // ---- flush the tile ---------------------------------------------------------
     for (int i = threadIdx.x; i < TW * TH; i += blockDim.x) {
         const int v = tile[i];
         if (v) {
             const int iy = i / TW, ix = i - iy * TW;
-            const int wx = ix + tx0 - wox, wy = iy + ty0 - woy;
-            if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
-                atomicAdd(&a.d_win[((size_t)s_local * a.win_h + wy) * a.win_w + wx], v);
-            else
-                atomicAdd((unsigned long long *)a.d_lost, (unsigned long long)v);
+            if (DIRECT) {
+                deposit(ga, ds, ix + tx0, iy + ty0, v);
+            } else {
+                const int wx = ix + tx0 - wox, wy = iy + ty0 - woy;
+                if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
+                    atomicAdd(&a.d_win[((size_t)s_local * a.win_h + wy) * a.win_w + wx], v);
+                else
+                    atomicAdd((unsigned long long *)a.d_lost, (unsigned long long)v);
+            }
         }
     }
 }

@@ -150,7 +150,14 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
             if (PASS != 2) {
                 const double dt = a.d_dt[r];
                 double acc[2], dn[2] = {0, 0}, ds[2] = {0, 0};
-                load_pair(a.d_acc + (size_t)r * plane, p, acc);
+                if (a.acc_fixed) {
+                    const longlong2 q = *reinterpret_cast<const longlong2 *>(
+                        reinterpret_cast<const long long *>(a.d_acc) + (size_t)r * plane + p);
+                    acc[0] = (double)q.x * (1.0 / 16777216.0);
+                    acc[1] = (double)q.y * (1.0 / 16777216.0);
+                } else {
+                    load_pair(reinterpret_cast<const double *>(a.d_acc) + (size_t)r * plane, p, acc);
+                }
                 if (a.add_noise && a.d_draw_noise)
                     load_pair(a.d_draw_noise + (size_t)r * plane, p, dn);
                 if (a.add_sky && a.d_draw_sky)

@@ -60,12 +60,14 @@ static int launch_throw(const PhotonParams &p, cudaStream_t st)
     return WB200_OK;
 }
 
-static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st)
+static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st,
+                         const wb200_gather_args *direct = nullptr)
 {
     WB_REQUIRE(a != nullptr, "null args");
     WB_REQUIRE(a->n_samples >= 0 && a->n_bins > 0, "bad sizes");
     WB_REQUIRE(a->chunk_bins > 0 && (a->chunk_bins % 32) == 0, "chunk_bins must be a multiple of 32");
-    WB_REQUIRE(a->d_counts && a->d_win && a->d_win_ox && a->d_win_oy && a->d_lost, "null buffer");
+    WB_REQUIRE(a->d_counts, "null counts");
+    WB_REQUIRE(direct || (a->d_win && a->d_win_ox && a->d_win_oy && a->d_lost), "null window buffers");
     WB_REQUIRE(a->d_ratio && a->d_sigl && a->d_sigh, "null psf tables");
     WB_REQUIRE((a->d_xpos && a->d_ypos) || (a->d_trace && a->d_wl), "no positions");
     WB_REQUIRE(a->n_samples <= 65535, "at most 65535 sub-samples per launch");
@@ -74,9 +76,10 @@ static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t s
     PhotonParams p;
     p.a = *a;
     p.sample0 = sample0;
+    WB_REQUIRE(!direct || a->rng_mode == WB200_RNG_PHILOX, "direct accumulation is a native-mode path");
     switch (a->rng_mode) {
     case WB200_RNG_PHILOX: {
-        if (getenv("WB200_GENERIC_THROW"))      // A/B switch: the baseline generic kernel
+        if (getenv("WB200_GENERIC_THROW") && !direct)      // A/B switch: the baseline generic kernel
             return launch_throw<WB200_RNG_PHILOX>(p, st);
         PhiloxKeys keys;
         uint32_t k0 = a->key0, k1 = a->key1;
@@ -88,7 +91,14 @@ static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t s
         }
         const int chunks = (a->n_bins + a->chunk_bins - 1) / a->chunk_bins;
         dim3 grid(chunks, a->n_samples);
-        k_throw_philox<TILE_W, TILE_H><<<grid, 256, (size_t)TILE_W * TILE_H * sizeof(int), st>>>(p, keys);
+        const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int);
+        if (direct) {
+            k_throw_philox<TILE_W, TILE_H, true><<<grid, 256, smem, st>>>(p, keys, *direct);
+        } else {
+            wb200_gather_args none;
+            memset(&none, 0, sizeof(none));
+            k_throw_philox<TILE_W, TILE_H, false><<<grid, 256, smem, st>>>(p, keys, none);
+        }
         WB_LAUNCHED("k_throw_philox");
         return WB200_OK;
     }
@@ -229,6 +239,17 @@ int wb200_throw_photons(const wb200_photon_args *args, void *stream)
 int wb200_throw_photons_at(const wb200_photon_args *args, int sample0, void *stream)
 {
     return throw_photons(args, sample0, (cudaStream_t)stream);
+}
+
+int wb200_throw_photons_direct(const wb200_photon_args *args, const wb200_gather_args *g,
+                               int sample0, void *stream)
+{
+    WB_REQUIRE(args && g, "null args");
+    WB_REQUIRE(g->n_reads > 0 && g->L > 0 && g->F >= g->L && g->d_read_end && g->d_acc, "bad geometry");
+    WB_REQUIRE(args->d_trace, "direct accumulation needs the trace table");
+    WB_REQUIRE(!g->add_flat || (g->d_flat[0] && g->d_flat[1] && g->d_flat[2] && g->d_flat[3]),
+               "flat planes missing");
+    return throw_photons(args, sample0, (cudaStream_t)stream, g);
 }
 
 int wb200_gather_flat(const wb200_gather_args *a, void *stream)

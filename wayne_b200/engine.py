@@ -416,13 +416,73 @@ class ExposureRun(object):
             chunk = min(chunk, max(32, int(math.ceil(self.W / per / 32.0)) * 32))
         return ox.astype(np.int32), oy.astype(np.int32), ww, wh, chunk
 
+    def _gather_args(self, add_flat):
+        """Geometry + flat planes shared by wb200_gather_flat and the direct thrower."""
+        g = self.grism
+        ga = _lib.GatherArgs()
+        ga.n_reads = self.R
+        ga.L, ga.F, ga.border = self.L, self.F, BORDER
+        ga.add_flat = 1 if add_flat else 0
+        ga.flat_off = g.flat_offset(self.S)
+        ga.flat_n = 1014
+        keep = None
+        if add_flat:
+            fl = g._load_flat()
+            keep = self.e.cached_plane(("flat", g.name, g.flat_file_name), lambda: tuple(
+                self.e.to_dev(p, np.float64) for p in fl['f']))
+            ga.flat_n = int(fl['f'][0].shape[0])
+            ga.flat_f32 = 1 if fl['f'][0].dtype.itemsize == 4 else 0
+            ga.flat_wmin, ga.flat_wmax = float(fl['wmin']), float(fl['wmax'])
+            for i in range(4):
+                ga.d_flat[i] = keep[i].data_ptr()
+        ga.d_read_end = self.d_read_end.data_ptr()
+        return ga, keep
+
+    def throw_direct(self, key=(0, 0), add_flat=True):
+        """Native mode, stages 2+3+3b in one launch: Philox electrons binned in
+        shared-memory tiles, flat applied at tile flush, accumulated into int64
+        fixed-point interval planes (no per-sub-sample windows, no gather pass)."""
+        e = self.e
+        if self.d_counts is None:
+            raise RuntimeError("counts() must run before throw_direct()")
+        N, W, L, F = self.N, self.W, self.L, self.F
+        self.d_acc = e.zeros((self.R, F, F), torch.int64)
+        self.acc_fixed = True
+        _, _, ww, wh, chunk = self._window_geometry(ZMAX[_lib.RNG_PHILOX])
+        self.win_geometry = (ww, wh, chunk)
+        pa = _lib.PhotonArgs()
+        pa.n_samples, pa.n_bins, pa.chunk_bins = N, W, chunk
+        pa.nr, pa.nc = L, L
+        pa.rng_mode = _lib.RNG_PHILOX
+        pa.sub_scale = self.sub_scale
+        pa.key0, pa.key1 = key[0] & 0xffffffff, key[1] & 0xffffffff
+        pa.d_counts = self.d_counts.data_ptr()
+        pa.d_totals = self.d_totals.data_ptr()
+        pa.d_trace = self.d_trace.data_ptr()
+        pa.d_wl = self.d_wl.data_ptr()
+        pa.d_ratio, pa.d_sigl, pa.d_sigh = (self.d_ratio.data_ptr(), self.d_sigl.data_ptr(),
+                                            self.d_sigh.data_ptr())
+        ga, keep = self._gather_args(add_flat)
+        ga.n_samples, ga.sample0 = N, 0
+        ga.d_trace = self.d_trace.data_ptr()
+        ga.d_acc = self.d_acc.data_ptr()
+        e.mark('k_throw', True)
+        check(lib.wb200_throw_photons_direct(C.byref(pa), C.byref(ga), 0, e.stream_ptr()),
+              "wb200_throw_photons_direct")
+        e.mark('k_throw', False)
+        self._keep = (keep,)
+        return self.d_acc
+
     def throw(self, rng_mode, key=(0, 0), seeds=None, threads=1, normals=None, add_flat=True,
               window_cap=WINDOW_BYTES_CAP):
-        """Stages 2+3 (+3b): throw and bin every electron, then flat-field and
-        accumulate into the per-read-interval planes ``acc``."""
+        """Stages 2+3 (+3b): throw and bin every electron into per-sub-sample HBM
+        windows, then flat-field and accumulate IN SUB-SAMPLE ORDER into the
+        float64 per-read-interval planes ``acc`` (the parity path; native mode
+        uses throw_direct)."""
         e = self.e
         st = e.stream_ptr()
         N, W, L, F = self.N, self.W, self.L, self.F
+        self.acc_fixed = False
         if self.d_counts is None:
             raise RuntimeError("counts() must run before throw()")
         d_off = d_seeds = d_norm = d_nbase = None
@@ -559,6 +619,7 @@ class ExposureRun(object):
         a.sky_rate = float(sky_rate or 0.0)
         a.sky_f32 = 1 if sky_f32 else 0
         a.fast_math = 1 if fast_math else 0
+        a.acc_fixed = 1 if getattr(self, 'acc_fixed', False) else 0
         a.const_gain = float(const_gain)
         a.clip_lo, a.clip_hi = (float(clip[0]), float(clip[1])) if clip is not None else (0.0, 0.0)
         a.read_noise = float(read_noise or 0.0)

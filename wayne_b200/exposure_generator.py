@@ -388,7 +388,10 @@ class ExposureGenerator(object):
                 rows, cols = np.concatenate(rows), np.concatenate(cols)
                 cosmics = ((rows + BORDER) * F + (cols + BORDER), np.concatenate(rd),
                            np.concatenate(en))
-            run.throw(_lib.RNG_PHILOX, key=key, add_flat=add_flat)
+            if params.direct_accumulation:
+                run.throw_direct(key=key, add_flat=add_flat)
+            else:
+                run.throw(_lib.RNG_PHILOX, key=key, add_flat=add_flat)
 
         sky_p, gain_p, nl_p, zero_p = self._device_planes(
             eng, add_gain_variations, sky_rate, add_non_linear, zero_read)

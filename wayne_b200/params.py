@@ -20,6 +20,11 @@ seed = None  # set by the visit driver (wayne/params.py:60, run_visit.py:69-77)
 # based) or 'numpy' (compat: the reference's numpy + rand_r streams)
 rng = os.environ.get("WAYNE_B200_RNG", "philox")
 
+# native mode: fuse flat field + accumulation into the photon kernel's tile flush
+# (int64 fixed-point interval planes).  Off = per-sub-sample windows + ordered
+# gather, the path the parity mode always uses.
+direct_accumulation = os.environ.get("WAYNE_B200_DIRECT", "1") != "0"
+
 
 def set_calibration_dir(path):
     """Point the package at a calibration directory (affects objects built afterwards)."""
