@@ -186,4 +186,70 @@ __device__ inline long long poisson_draw(PhiloxStream &g, double lam)
     }
 }
 
+// The same PTRS sampler with the expensive pieces in fp32 on the SFU -- used by
+// the native kernels, where only the DISTRIBUTION matters (tests/test_rng_gpu.py
+// checks it against the exact pmf by chi-square):
+//   * the proposal constants (sqrt, reciprocals) and 2a/us are fp32; the same
+//     rounded values enter both the proposal and the acceptance test;
+//   * U, V, us and k stay fp64 (exact uniforms, integer-exact k for any lam);
+//   * the acceptance test's right-hand side is rewritten around m = k+1 as
+//       (m - lam) - k*log1p((m-lam)/lam) - 0.5*log(m) - C - Stirling(1/m),
+//     whose fp32 rounding error scales with |m - lam| ~ sqrt(lam) rather than
+//     with lam*log(lam), so lg2.approx is accurate enough (error <~ 1e-5).
+// lam >= 4e6 (never reached by photon counts per cell in practice) and lam < 10
+// use the fp64 sampler above.
+__device__ __forceinline__ float log1p_f(float d)
+{
+    const float u = 1.0f + d;
+    const float lu = __logf(u);
+    // Kahan: log1p(d) = log(u) * d / (u - 1) restores the bits lost in 1 + d
+    return (u == 1.0f) ? d : lu * __fdividef(d, u - 1.0f);
+}
+
+__device__ inline long long poisson_draw_fast(PhiloxStream &g, double lam)
+{
+    if (!(lam >= 10.0) || lam >= 4.0e6)
+        return poisson_draw(g, lam);
+    const float lamf = (float)lam;
+    float slam;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(slam) : "f"(lamf));
+    const float b = fmaf(2.53f, slam, 0.931f);
+    const float a = fmaf(0.02483f, b, -0.059f);
+    const float vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
+    const float two_a = 2.0f * a;
+    float invalpha = 0.f, inv_lam = 0.f;
+    bool have = false;
+    for (;;) {
+        const double U = g.uniform() - 0.5;
+        const double V = g.uniform();
+        const double us = 0.5 - fabs(U);
+        const float usf = (float)us;
+        const float t = fmaf(__fdividef(two_a, usf), (float)U, b * (float)U);
+        const double kf = floor((double)t + lam + 0.43);
+        if (usf >= 0.07f && (float)V <= vr)
+            return (long long)kf;
+        if (kf < 0.0 || (usf < 0.013f && V > us))
+            continue;
+        if (!have) {
+            invalpha = 1.1239f + __fdividef(1.1328f, b - 3.4f);
+            inv_lam = __fdividef(1.0f, lamf);
+            have = true;
+        }
+        const float lhs = __logf(__fdividef((float)V * invalpha, fmaf(a, __fdividef(1.0f, usf * usf), b)));
+        const double m = kf + 1.0;
+        const float dm = (float)(m - lam);          // exact difference, then rounded
+        const float mf = (float)m;
+        const float xi = __fdividef(1.0f, mf), xi2 = xi * xi;
+        float rhs;
+        if (kf < 10.0) {                            // lam >= 10 makes this rare; exact table
+            rhs = (float)(-lam + kf * log(lam) - log_factorial(kf));
+        } else {
+            const float series = xi * (8.333333333e-2f - xi2 * (2.777777778e-3f - xi2 * 7.936507937e-4f));
+            rhs = dm - (float)kf * log1p_f(dm * inv_lam) - 0.5f * __logf(mf) - 0.9189385332f - series;
+        }
+        if (lhs <= rhs)
+            return (long long)kf;
+    }
+}
+
 } // namespace wb

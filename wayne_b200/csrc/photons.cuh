@@ -454,7 +454,7 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
 }
 
 template <int TW, int TH, bool DIRECT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_args ga)
 {
     const wb200_photon_args &a = p.a;
@@ -629,24 +629,34 @@ k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_a
             }
             const uint4 r = philox4x32_10_keys(
                 make_uint4((uint32_t)j, (uint32_t)(wb + b), s_glob, WB_STREAM_PHOTONS), keys);
+            // both electrons of the unit in straight-line code (their MUFU chains
+            // interleave); the second is masked off for an odd count's last unit
+            const int k0 = 2 * j;
+            const bool two = (k0 + 1) < cur.cnt;
+            const float u1a = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+            const float u1b = fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+            const float tha = fmaf((float)r.y, 1.4629180792671596e-09f, -3.14159265358979f);
+            const float thb = fmaf((float)r.w, 1.4629180792671596e-09f, -3.14159265358979f);
+            const float rsa = sqrt_approx(-1.3862943611198906f * lg2_approx(u1a)) *
+                              ((k0 < cur.nh) ? cur.sh : cur.sl);
+            const float rsb = sqrt_approx(-1.3862943611198906f * lg2_approx(u1b)) *
+                              ((k0 + 1 < cur.nh) ? cur.sh : cur.sl);
+            const int ixa = floor_magic(fmaf(cos_approx(tha), rsa, cur.fx));
+            const int iya = floor_magic(fmaf(sin_approx(tha), rsa, cur.fy));
+            const int ixb = floor_magic(fmaf(cos_approx(thb), rsb, cur.fx));
+            const int iyb = floor_magic(fmaf(sin_approx(thb), rsb, cur.fy));
+            const bool ina = (unsigned)ixa < nx && (unsigned)iya < ny;
+            const bool inb = (unsigned)ixb < nx && (unsigned)iyb < ny;
+            if (ina)
+                red_shared_inc(tile_acc + (uint32_t)(iya * (TW * 4) + ixa * 4));
+            if (inb && two)
+                red_shared_inc(tile_acc + (uint32_t)(iyb * (TW * 4) + ixb * 4));
+            if (!ina || (two && !inb)) { // rare: electrons that left the tile
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k = 2 * j + h;
-                if (k >= cur.cnt)
-                    break;
-                const uint32_t ra = h ? r.z : r.x, rb = h ? r.w : r.y;
-                // Box-Muller: u1 in (0,1], theta in (-pi, pi)
-                const float u1 = fmaf((float)ra, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-                const float th = fmaf((float)rb, 1.4629180792671596e-09f, -3.14159265358979f);
-                const float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
-                const float sg = (k < cur.nh) ? cur.sh : cur.sl;
-                const float rs = rad * sg;
-                const int ix = floor_magic(fmaf(cos_approx(th), rs, cur.fx));
-                const int iy = floor_magic(fmaf(sin_approx(th), rs, cur.fy));
-                if ((unsigned)ix < nx && (unsigned)iy < ny) {
-                    red_shared_inc(tile_acc + (uint32_t)(iy * (TW * 4) + ix * 4));
-                } else {
-                    const int xa = ix + ax0, ya = iy + ay0;
+                for (int h = 0; h < 2; ++h) {
+                    if (h ? (!two || inb) : ina)
+                        continue;
+                    const int xa = (h ? ixb : ixa) + ax0, ya = (h ? iyb : iya) + ay0;
                     if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
                         if (DIRECT)
                             deposit(ga, ds, xa, ya, 1);

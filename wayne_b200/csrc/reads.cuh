@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                                 const double lam = a.sky_f32
                                     ? (double)__fmul_rn(__double2float_rn(sky[h]), __double2float_rn(bg))
                                     : sky[h] * bg;
-                                px = px + (double)poisson_draw(g, lam);
+                                px = px + (double)(FAST ? poisson_draw_fast(g, lam) : poisson_draw(g, lam));
                             }
                         }
                         if (chead[h] >= 0) {

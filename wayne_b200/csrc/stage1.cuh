@@ -191,7 +191,7 @@ k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict
             c = (long long)rint(e);
         } else if (mode == WB200_COUNT_POISSON) {
             PhiloxStream g(k0, k1, (uint32_t)w, (uint32_t)s, WB_STREAM_COUNTS);
-            c = poisson_draw(g, e);
+            c = poisson_draw_fast(g, e);
         } else if (counts) {
             c = counts[(size_t)s * W + w];
         }
