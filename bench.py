@@ -279,6 +279,9 @@ def run_native(args, wk):
     from wayne_b200 import _lib
     from wayne_b200.engine import DeviceEngine
     eng = DeviceEngine.get(local)
+    if os.environ.get('WB200_HOSTTRACE'):
+        from tools import hosttrace
+        hosttrace.install()
     inp = make_inputs(wk)
     N, W = len(inp['read_index']) and len(np.asarray(u.value_in(inp['mid'], u.ms))), len(inp['wl'])
 
@@ -317,9 +320,13 @@ def run_native(args, wk):
     # is outside the timed region; its samples are reset when the clock starts)
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('WB200_NO_CLOCKS')) else None
     eng.profile = True               # stage events on in the warm-up too (first-use costs)
-    for i in range(args.warmup):
+    phot_acc = torch.zeros((), dtype=torch.int64, device=dev)
+    lost_acc = torch.zeros((1,), dtype=torch.int64, device=dev)
+    n_warm = max(args.warmup, 8)     # long enough for the allocator pools to become stationary
+    for i in range(n_warm):
         eg, _ = one(i, True)
-        _ = eg._run.d_totals.sum() + eg._run.lost.sum()   # load the bookkeeping kernels now
+        phot_acc += eg._run.d_totals.sum()           # same bookkeeping as the timed loop
+        lost_acc += eg._run.lost
         del eg
     barrier()
     if sampler:
@@ -329,14 +336,17 @@ def run_native(args, wk):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st = torch.cuda.current_stream(dev)
+    phot_acc.zero_()
+    lost_acc.zero_()
+    torch.cuda.synchronize(dev)
+    if os.environ.get('WB200_HOSTTRACE'):
+        sys.stderr.write('[hosttrace] t=%.1f VALUE REGION START\n' % (time.perf_counter() * 1e3 % 1e6))
     e0.record(st)
-    phot_acc = torch.zeros((), dtype=torch.int64, device=dev)
-    lost_acc = torch.zeros((1,), dtype=torch.int64, device=dev)
     geom = None
     v_issue = []
     for i in range(args.steps):
         ta = time.perf_counter()
-        eg, _ = one(args.warmup + i, True)
+        eg, _ = one(n_warm + i, True)
         v_issue.append((time.perf_counter() - ta) * 1e3)
         phot_acc += eg._run.d_totals.sum()       # device-side bookkeeping, no sync
         lost_acc += eg._run.lost
@@ -345,6 +355,8 @@ def run_native(args, wk):
     e1.record(st)
     barrier()
     launches = _lib.launch_count() - l0
+    if os.environ.get('WB200_HOSTTRACE'):
+        sys.stderr.write('[hosttrace] t=%.1f VALUE REGION END\n' % (time.perf_counter() * 1e3 % 1e6))
     ms_value = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     stages = eng.stage_times()
     eng.profile = False
@@ -355,31 +367,32 @@ def run_native(args, wk):
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside ---------------
     import collections
-    warm = [one(i, False)[1] for i in range(max(6, args.warmup))]   # fills the pinned-buffer pool
-    for w_ in warm:
-        w_.reads
-    del warm
+
+    def pipeline(first, n):
+        """n exposures through the public API; every exposure's reads are touched
+        on the host (two exposures behind the one being issued)."""
+        pending = collections.deque()
+        t_issue, t_wait, d2h, checksum = [], [], 0, 0.0
+        for i in range(n):
+            ta = time.perf_counter()
+            _, exp = one(first + i, False)
+            tb = time.perf_counter()
+            pending.append(exp)
+            while len(pending) > 2 or (i == n - 1 and pending):
+                reads = pending.popleft().reads
+                d2h = sum(r[0].nbytes for r in reads)
+                checksum += float(reads[-1][0][512 % reads[-1][0].shape[0], 7])
+            t_issue.append((tb - ta) * 1e3)
+            t_wait.append((time.perf_counter() - tb) * 1e3)
+        torch.cuda.synchronize(dev)
+        return t_issue, t_wait, d2h, checksum
+
+    pipeline(0, max(12, args.warmup))        # warm-up: same pipeline, fills the pinned / device pools
     barrier()
+    if os.environ.get('WB200_HOSTTRACE'):
+        sys.stderr.write('[hosttrace] t=%.1f E2E REGION START\n' % (time.perf_counter() * 1e3 % 1e6))
     t0 = time.perf_counter()
-    d2h = 0
-    pending = collections.deque()
-    checksum = 0.0
-    t_issue, t_wait = [], []
-    for i in range(args.steps):
-        ta = time.perf_counter()
-        _, exp = one(args.warmup + i, False)
-        tb = time.perf_counter()
-        pending.append(exp)
-        while len(pending) > 2:              # the consumer: read every exposure's result on the host
-            reads = pending.popleft().reads
-            d2h = sum(r[0].nbytes for r in reads)
-            checksum += float(reads[-1][0][512 % reads[-1][0].shape[0], 7])
-        t_issue.append((tb - ta) * 1e3)
-        t_wait.append((time.perf_counter() - tb) * 1e3)
-    while pending:
-        reads = pending.popleft().reads
-        d2h = sum(r[0].nbytes for r in reads)
-        checksum += float(reads[-1][0][512 % reads[-1][0].shape[0], 7])
+    t_issue, t_wait, d2h, checksum = pipeline(n_warm, args.steps)
     torch.cuda.synchronize(dev)
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     h2d = depth_host.nbytes + inp['flux'].nbytes + inp['wl'].nbytes + 3 * 8 * N
@@ -426,7 +439,7 @@ def run_native(args, wk):
     dominant = max(stages.items(), key=lambda kv: kv[1][0])[0]
     line = {
         'metric': 'exposures_per_s', 'value': world * 1e3 / ms_value, 'unit': 'exposures/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_value,
+        'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_value,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'photons_per_exposure': photons,
         'photons_per_s': world * photons * 1e3 / ms_value,
@@ -437,7 +450,8 @@ def run_native(args, wk):
         'e2e': {'value': world * 1e3 / ms_e2e, 'unit': 'exposures/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'host_issue_ms': [round(float(np.median(t_issue)), 3), round(float(np.max(t_issue)), 3)],
-                'host_wait_ms': [round(float(np.median(t_wait)), 3), round(float(np.max(t_wait)), 3)]},
+                'host_wait_ms': [round(float(np.median(t_wait)), 3), round(float(np.max(t_wait)), 3)],
+                'host_step_ms': [round(a_ + b_, 2) for a_, b_ in zip(t_issue, t_wait)]},
         'gpu_launches': int(launches),
         'host_issue_ms': [round(float(np.median(v_issue)), 3), round(float(np.max(v_issue)), 3)],
         'stage_ms': {k: v[0] / args.steps for k, v in stages.items()},

@@ -51,7 +51,11 @@ __device__ inline double interp1(double x, const double *xp, const double *fp, i
 }
 
 // grism.py:111-118 (+ tools.py:106-128): one thread per wavelength bin.
-__global__ void k_bin_tables(int W, const double *__restrict__ wl, const double *poly12, int ns,
+struct Poly12 {
+    double c[12];
+};
+
+__global__ void k_bin_tables(int W, const double *__restrict__ wl, const Poly12 poly, int ns,
                              const double *__restrict__ sens_wl,
                              const double *__restrict__ sens_val, double *ratio, double *sigl,
                              double *sigh, double *sens, double *dwl)
@@ -60,9 +64,9 @@ __global__ void k_bin_tables(int W, const double *__restrict__ wl, const double 
     if (w >= W)
         return;
     const double x = wl[w];
-    ratio[w] = polyval4(poly12 + 0, x);
-    sigl[w] = polyval4(poly12 + 4, x);
-    sigh[w] = polyval4(poly12 + 8, x);
+    ratio[w] = polyval4(poly.c + 0, x);
+    sigl[w] = polyval4(poly.c + 4, x);
+    sigh[w] = polyval4(poly.c + 8, x);
     sens[w] = interp1(x, sens_wl, sens_val, ns);
     // bin_centers_to_widths: half-gap to the previous centre (first bin reuses
     // the second's) plus half-gap to the next centre (last bin reuses its own).

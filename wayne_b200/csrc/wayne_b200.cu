@@ -158,17 +158,13 @@ int wb200_bin_tables(int n_bins, const double *d_wl, const double *psf_poly12, i
     WB_REQUIRE(n_bins >= 2 && n_sens >= 1, "need >= 2 bins and a sensitivity table");
     WB_REQUIRE(d_wl && psf_poly12 && d_sens_wl && d_sens_val, "null input");
     WB_REQUIRE(d_ratio && d_sigl && d_sigh && d_sens && d_dwl, "null output");
-    cudaStream_t st = (cudaStream_t)stream;
-    // the 12 polynomial coefficients are a HOST array: stage them in a small
-    // device buffer that lives for the duration of the (stream-ordered) launch
-    double *d_poly = nullptr;
-    WB_CUDA(cudaMallocAsync(&d_poly, 12 * sizeof(double), st));
-    WB_CUDA(cudaMemcpyAsync(d_poly, psf_poly12, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_bin_tables<<<(n_bins + 127) / 128, 128, 0, st>>>(n_bins, d_wl, d_poly, n_sens, d_sens_wl,
-                                                       d_sens_val, d_ratio, d_sigl, d_sigh, d_sens,
-                                                       d_dwl);
+    // the 12 polynomial coefficients are a HOST array: they travel by value as a
+    // kernel parameter (no staging allocation, no copy)
+    Poly12 poly;
+    memcpy(poly.c, psf_poly12, sizeof(poly.c));
+    k_bin_tables<<<(n_bins + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        n_bins, d_wl, poly, n_sens, d_sens_wl, d_sens_val, d_ratio, d_sigl, d_sigh, d_sens, d_dwl);
     WB_LAUNCHED("k_bin_tables");
-    WB_CUDA(cudaFreeAsync(d_poly, st));
     return WB200_OK;
 }
 

@@ -162,6 +162,22 @@ class DeviceEngine(object):
         t.record_stream(cur)
         return t
 
+    def admit(self):
+        """Called at the start of an exposure: wait until fewer than MAX_IN_FLIGHT
+        earlier exposures are still executing.  Bounds the host's run-ahead (and
+        with it HBM and pinned-memory use: ~1 GB per exposure in flight) without
+        ever letting the GPU run dry -- issuing an exposure costs the host less
+        than executing one costs the GPU."""
+        while len(self._in_flight) >= self.MAX_IN_FLIGHT:
+            self._in_flight.pop(0).synchronize()
+
+    def retire(self, event=None):
+        """Called when an exposure's last operation has been queued."""
+        if event is None:
+            event = torch.cuda.Event()
+            event.record(torch.cuda.current_stream(self.device))
+        self._in_flight.append(event)
+
     def fetch_async(self, dev_tensor, small=None):
         """Queue the device->host copy of ``dev_tensor`` (and of an optional small
         tensor, e.g. a status word) on the copy stream behind everything already on
@@ -183,9 +199,7 @@ class DeviceEngine(object):
         dev_tensor.record_stream(cs)
         done = torch.cuda.Event()
         done.record(cs)
-        self._in_flight.append(done)
-        while len(self._in_flight) > self.MAX_IN_FLIGHT:
-            self._in_flight.pop(0).synchronize()
+        self.retire(done)
         return done, arr, small_host
 
     def fetch(self, dev_tensor):
@@ -234,8 +248,14 @@ class ExposureRun(object):
     """One exposure's device state, built stage by stage."""
 
     def __init__(self, engine, grism, subarray, wl_um, flux, depth, depth_col0, xr, yr, dur_ms,
-                 scale, read_end):
+                 scale, read_end, aux=None):
         """
+        aux                  {name: small host array} uploaded with the other small
+                             inputs in the exposure's FIRST host->device copy
+                             (device views in ``self.aux``).  Small copies issued
+                             later would queue on the copy engine behind the next
+                             exposure's planet-signal upload and stall this
+                             exposure's per-pixel pass.
         wl_um, flux [W]      cropped wavelength grid [micron] and stellar flux on it
         depth [N][>=W] / None planet signal rows; columns depth_col0.. are used
         xr, yr, dur_ms [N]   sub-sample reference positions [px] and durations [ms]
@@ -265,11 +285,15 @@ class ExposureRun(object):
         flux_is_dev = isinstance(flux, torch.Tensor)
         small = [self.wl_host, self.xr_host, self.yr_host, np.ascontiguousarray(dur_ms, dtype=np.float64),
                  self.read_end_host]
+        aux = dict(aux or {})
+        aux_names = sorted(aux)
+        small += [aux[k] for k in aux_names]
         if not flux_is_dev:
             small.append(np.ascontiguousarray(flux, dtype=np.float64))
         packed = e.to_dev_many(small)
         self.d_wl, self.d_xr, self.d_yr, self.d_dur, self.d_read_end = packed[:5]
-        self.d_flux = e.to_dev(flux) if flux_is_dev else packed[5]
+        self.aux = dict(zip(aux_names, packed[5:5 + len(aux_names)]))
+        self.d_flux = e.to_dev(flux) if flux_is_dev else packed[-1]
         if depth is not None:
             if not isinstance(depth, torch.Tensor):
                 depth = np.asarray(depth)
@@ -624,7 +648,7 @@ class ExposureRun(object):
         a.clip_lo, a.clip_hi = (float(clip[0]), float(clip[1])) if clip is not None else (0.0, 0.0)
         a.read_noise = float(read_noise or 0.0)
         keep = []
-        d_dt = e.to_dev(dt_s, np.float64)
+        d_dt = dt_s if isinstance(dt_s, torch.Tensor) else e.to_dev(dt_s, np.float64)
         a.d_dt = d_dt.data_ptr()
         a.d_acc = self.d_acc.data_ptr()
         a.d_sky = sky_plane.data_ptr() if sky_plane is not None else None
@@ -653,9 +677,12 @@ class ExposureRun(object):
                 setattr(a, field, t.data_ptr())
         if cosmics is not None and len(cosmics[0]):
             pix, rd, en = cosmics
-            d_pix, d_rd, d_en = e.to_dev_many([np.asarray(pix, dtype=np.int32),
-                                               np.asarray(rd, dtype=np.int32),
-                                               np.asarray(en, dtype=np.float64)])
+            if isinstance(pix, torch.Tensor):
+                d_pix, d_rd, d_en = pix, rd, en
+            else:
+                d_pix, d_rd, d_en = e.to_dev_many([np.asarray(pix, dtype=np.int32),
+                                                   np.asarray(rd, dtype=np.int32),
+                                                   np.asarray(en, dtype=np.float64)])
             d_head = e.empty((F * F,), torch.int32)
             d_next = e.empty((len(pix),), torch.int32)
             check(lib.wb200_cosmic_chains(len(pix), _ptr(d_pix), F * F, _ptr(d_head), _ptr(d_next),

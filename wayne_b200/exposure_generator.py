@@ -281,6 +281,7 @@ class ExposureGenerator(object):
         key = tuple(int(k) for k in (rng_key if rng_key is not None else self._default_key(compat)))
 
         eng = DeviceEngine.get(self.device)
+        eng.admit()
 
         # ---- per-sub-sample seeds and pointing jitter (:327-329) ---------------
         if compat:
@@ -305,9 +306,28 @@ class ExposureGenerator(object):
             if depth.ndim != 2 or depth.shape[0] < num_samples:
                 raise ValueError("planet_signal must be [n_samples][n_wl]")
             depth = depth[:num_samples]
+        aux = {'dt': dt_s}
+        native_cosmics = None
+        if not compat and cosmic_rate is not None:
+            # hit list of the whole exposure (cosmic_rays.py:88-139 per read interval),
+            # drawn up front so it rides in the exposure's first small upload
+            g = np.random.Generator(np.random.Philox(key=((key[0] << 32) | key[1]) ^ 0xC05B1C))
+            rd, rows, cols, en = [], [], [], []
+            for r in range(R):
+                n = g.poisson(cosmic_rate / (1024. * 1024.) * (L * L) * dt_s[r])
+                rd.append(np.full(n, r, np.int32))
+                en.append(g.integers(10000, 35000, n).astype(np.float64))
+                rows.append(g.integers(0, L, n))
+                cols.append(g.integers(0, L, n))
+            rows, cols = np.concatenate(rows), np.concatenate(cols)
+            if len(rows):
+                aux['cos_pix'] = ((rows + BORDER) * F + (cols + BORDER)).astype(np.int32)
+                aux['cos_rd'] = np.concatenate(rd)
+                aux['cos_en'] = np.concatenate(en)
+                native_cosmics = True
         run = ExposureRun(eng, self.grism, S, wl_um[i0:i1], flux, depth, i0,
                           x_ref + s_x_jitter, s_y_refs + s_y_jitter, dur_ms, scale_factor,
-                          np.asarray(read_index, dtype=np.int32))
+                          np.asarray(read_index, dtype=np.int32), aux=aux)
         self._run = run
 
         draws = {}
@@ -376,18 +396,8 @@ class ExposureGenerator(object):
             run.throw(_lib.RNG_RANDR, seeds=s_rand_seeds, threads=threads, add_flat=add_flat)
         else:
             run.counts(_lib.COUNT_POISSON if add_stellar_noise else _lib.COUNT_ROUND, key=key)
-            if cosmic_rate is not None:
-                g = np.random.Generator(np.random.Philox(key=((key[0] << 32) | key[1]) ^ 0xC05B1C))
-                rd, rows, cols, en = [], [], [], []
-                for r in range(R):
-                    n = g.poisson(cosmic_rate / (1024. * 1024.) * (L * L) * dt_s[r])
-                    rd.append(np.full(n, r, np.int32))
-                    en.append(g.integers(10000, 35000, n).astype(np.float64))
-                    rows.append(g.integers(0, L, n))
-                    cols.append(g.integers(0, L, n))
-                rows, cols = np.concatenate(rows), np.concatenate(cols)
-                cosmics = ((rows + BORDER) * F + (cols + BORDER), np.concatenate(rd),
-                           np.concatenate(en))
+            if native_cosmics:
+                cosmics = (run.aux['cos_pix'], run.aux['cos_rd'], run.aux['cos_en'])
             if params.direct_accumulation:
                 run.throw_direct(key=key, add_flat=add_flat)
             else:
@@ -396,7 +406,7 @@ class ExposureGenerator(object):
         sky_p, gain_p, nl_p, zero_p = self._device_planes(
             eng, add_gain_variations, sky_rate, add_non_linear, zero_read)
         out = run.reads(
-            dt_s, key=key, sky_rate=sky_rate, sky_plane=sky_p, gain_plane=gain_p, zero=zero_p,
+            run.aux['dt'], key=key, sky_rate=sky_rate, sky_plane=sky_p, gain_plane=gain_p, zero=zero_p,
             dark=d_dark, nl_planes=nl_p, noise=(noise_mean, noise_std) if use_noise else (0.0, 0.0),
             clip=(det.min_counts, det.max_counts) if clip_values_det_limits else None,
             read_noise=det.read_noise if add_read_noise else 0.0, cosmics=cosmics, draws=draws,
@@ -405,6 +415,7 @@ class ExposureGenerator(object):
             fast_math=not compat)
 
         if device_result:
+            eng.retire()
             self.exposure.device_reads = out
             self.exp_info['sim_time'] = (time.time() - start_time) * u.s
             return self.exposure
