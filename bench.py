@@ -329,6 +329,8 @@ def run_native(args, wk):
         lost_acc += eg._run.lost
         del eg
     barrier()
+    from wayne_b200.engine import tune_host
+    tune_host()                      # gc.freeze(): no 40 ms full-GC pauses inside the timed regions
     if sampler:
         sampler.reset()
     eng.profile = True
@@ -352,6 +354,9 @@ def run_native(args, wk):
         lost_acc += eg._run.lost
         geom = eg._run.win_geometry
         del eg
+        if os.environ.get('WB200_HOSTTRACE') and (time.perf_counter() - ta) * 1e3 > 8:
+            sys.stderr.write('[hosttrace] step %d: one() %.2f ms, whole iteration %.2f ms\n' % (
+                i, v_issue[-1], (time.perf_counter() - ta) * 1e3))
     e1.record(st)
     barrier()
     launches = _lib.launch_count() - l0
@@ -370,7 +375,7 @@ def run_native(args, wk):
 
     def pipeline(first, n):
         """n exposures through the public API; every exposure's reads are touched
-        on the host (two exposures behind the one being issued)."""
+        on the host (three exposures behind the one being issued)."""
         pending = collections.deque()
         t_issue, t_wait, d2h, checksum = [], [], 0, 0.0
         for i in range(n):
@@ -378,7 +383,7 @@ def run_native(args, wk):
             _, exp = one(first + i, False)
             tb = time.perf_counter()
             pending.append(exp)
-            while len(pending) > 2 or (i == n - 1 and pending):
+            while len(pending) > 3 or (i == n - 1 and pending):
                 reads = pending.popleft().reads
                 d2h = sum(r[0].nbytes for r in reads)
                 checksum += float(reads[-1][0][512 % reads[-1][0].shape[0], 7])

@@ -32,5 +32,17 @@ def install():
         wrap(engine.DeviceEngine, n)
     for n in ('__init__', 'counts', 'throw_direct', 'throw', 'reads', '_window_geometry', '_gather_args'):
         wrap(engine.ExposureRun, n)
-    for n in ('scanning_frame', '_device_planes', '_gen_zero_read'):
+    for n in ('scanning_frame', '_device_planes', '_gen_zero_read', '__init__', '_gen_scanning_sample_times'):
         wrap(exposure_generator.ExposureGenerator, n)
+    import gc
+    state = {}
+
+    def on_gc(phase, info):
+        if phase == 'start':
+            state['t'] = time.perf_counter()
+        else:
+            dt = (time.perf_counter() - state.get('t', time.perf_counter())) * 1e3
+            if dt >= thr:
+                sys.stderr.write('[hosttrace] t=%.1f gc gen%d %.2f ms (%d collected)\n' % (
+                    time.perf_counter() * 1e3 % 1e6, info.get('generation', -1), dt, info.get('collected', 0)))
+    gc.callbacks.append(on_gc)

@@ -46,6 +46,16 @@ def _dp(a):
     return a.ctypes.data_as(_lib.DP)
 
 
+def tune_host():
+    """Call once after start-up in a long-running driver: moves every object alive
+    now into the garbage collector's permanent generation (gc.freeze), so the
+    cyclic collector's full passes -- 40 ms each with torch imported, enough to
+    let the GPU run dry -- no longer rescan them while exposures are in flight."""
+    import gc
+    gc.collect()
+    gc.freeze()
+
+
 class DeviceEngine(object):
     """Per-GPU context: stream, resident calibration planes, scratch reuse."""
 
@@ -74,6 +84,7 @@ class DeviceEngine(object):
         self._copy_stream = None
         self._upload_stream = None
         self._in_flight = []
+        self._upload_rings = {}
 
     # -- helpers -----------------------------------------------------------
     def stream_ptr(self):
@@ -141,7 +152,7 @@ class DeviceEngine(object):
         out[BORDER:BORDER + n, BORDER:BORDER + n] = plane
         return out
 
-    MAX_IN_FLIGHT = 3      # device->host copies outstanding before the host waits
+    MAX_IN_FLIGHT = 4      # exposures in flight before the host waits (~1 GB of HBM each)
 
     def _streams(self):
         if self._copy_stream is None:
@@ -150,17 +161,41 @@ class DeviceEngine(object):
         return self._copy_stream, self._upload_stream
 
     def upload_async(self, host_array):
-        """Large host array -> device on the upload stream; the current stream
-        waits for it, so the copy of exposure i+1 overlaps the kernels of i."""
+        """Large host array -> device on the upload stream, into a ring of
+        persistent device buffers (one per exposure that may be in flight); the
+        current stream waits for the copy, so the upload of exposure i+1 overlaps
+        the kernels of exposure i.  Returns (tensor, slot); call
+        release_upload(slot) once the last kernel reading the tensor is queued.
+
+        A ring instead of the caching allocator: a freshly freed block is only
+        handed out again after the compute stream has drained, which serialised
+        the upload of the next exposure behind the current one."""
         _, up = self._streams()
         cur = torch.cuda.current_stream(self.device)
+        key = (tuple(host_array.shape), str(host_array.dtype))
+        ring = self._upload_rings.setdefault(key, {'bufs': [], 'free': [], 'next': 0})
+        n_slots = self.MAX_IN_FLIGHT + 1
+        slot = ring['next'] % n_slots
+        ring['next'] += 1
+        if slot >= len(ring['bufs']):
+            ring['bufs'].append(torch.empty(host_array.shape, dtype=self._TORCH_DT[host_array.dtype],
+                                            device=self.device))
+            ring['free'].append(None)
+        buf = ring['bufs'][slot]
         with torch.cuda.stream(up):
-            t = torch.from_numpy(host_array).to(self.device, non_blocking=True)
+            if ring['free'][slot] is not None:
+                up.wait_event(ring['free'][slot])      # previous user's kernels are done
+            buf.copy_(torch.from_numpy(host_array), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(up)
         cur.wait_event(ev)
-        t.record_stream(cur)
-        return t
+        return buf, (key, slot)
+
+    def release_upload(self, handle):
+        key, slot = handle
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._upload_rings[key]['free'][slot] = ev
 
     def admit(self):
         """Called at the start of an exposure: wait until fewer than MAX_IN_FLIGHT
@@ -302,11 +337,16 @@ class ExposureRun(object):
             elif depth.dtype != torch.float64:
                 raise ValueError("device planet_signal must be float64")
             big = (not isinstance(depth, torch.Tensor)) and depth.nbytes >= (8 << 20)
-            self.d_depth_full = e.upload_async(depth) if big else e.to_dev(depth)
+            self._depth_slot = None
+            if big:
+                self.d_depth_full, self._depth_slot = e.upload_async(depth)
+            else:
+                self.d_depth_full = e.to_dev(depth)
             self.depth_ld = int(depth.shape[1])
             self.depth_ptr = C.c_void_p(self.d_depth_full.data_ptr() + 8 * int(depth_col0))
         else:
             self.d_depth_full, self.depth_ld, self.depth_ptr = None, 0, None
+            self._depth_slot = None
 
         # ---- stage 1a: wavelength-only tables ---------------------------------
         tabs = e.empty((5, self.W))
@@ -334,6 +374,22 @@ class ExposureRun(object):
         self.d_expected = None
         self.d_acc = None
         self.lost = e.zeros((1,), torch.int64)
+
+    def _release_depth(self):
+        """The planet-signal upload buffer may be overwritten by a later exposure
+        once the kernels queued so far have run (k_counts is its only reader)."""
+        if self._depth_slot is not None:
+            self.e.release_upload(self._depth_slot)
+            self._depth_slot = None
+            self.d_depth_full = None
+            self.depth_ptr = None
+            self._depth_gone = True
+
+    def __del__(self):
+        try:
+            self._release_depth()
+        except Exception:      # interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------
     def tables_host(self):
@@ -379,9 +435,13 @@ class ExposureRun(object):
                                _ptr(self.d_counts), _ptr(self.d_totals), e.stream_ptr()),
               "wb200_counts")
         e.mark('k_counts', False)
+        self._release_depth()
 
     def expected_host(self):
         if self.d_expected is None:
+            if getattr(self, '_depth_gone', False):
+                raise RuntimeError("the planet-signal buffer of this exposure has been recycled; "
+                                   "call counts(..., want_expected=True) to keep the expected counts")
             self.d_expected = self.e.empty((self.N, self.W))
             check(lib.wb200_counts(self.N, self.W, _ptr(self.d_flux), self.depth_ptr,
                                    self.depth_ld, _ptr(self.d_sens), _ptr(self.d_dwl),
@@ -391,12 +451,14 @@ class ExposureRun(object):
         return self.d_expected.cpu().numpy()
 
     # ------------------------------------------------------------------
-    def _window_geometry(self, zmax):
+    def _window_geometry(self, zmax, stride=1):
         """Per-sub-sample HBM windows that are guaranteed to contain every
-        electron that lands inside the frame: trace extent +- zmax*sigma_max."""
+        electron that lands inside the frame: trace extent +- zmax*sigma_max.
+        ``stride`` > 1 evaluates every stride-th sub-sample only (enough for the
+        bins-per-CTA choice of the direct path, which has no windows)."""
         g = self.grism
         from .grism import wavelength_calibration_coeffs, ANGSTROM_TO_MICRON
-        x, y = self.xr_host, self.yr_host
+        x, y = self.xr_host[::stride], self.yr_host[::stride]
         m_t, c_t, m_w, c_w = wavelength_calibration_coeffs(x, y, g.trace_coeff, g.wl_solution)
         X0, X1 = x + 10, x + 20
         Y0 = m_t * (X0 - x) + c_t + y
@@ -472,7 +534,7 @@ class ExposureRun(object):
         N, W, L, F = self.N, self.W, self.L, self.F
         self.d_acc = e.zeros((self.R, F, F), torch.int64)
         self.acc_fixed = True
-        _, _, ww, wh, chunk = self._window_geometry(ZMAX[_lib.RNG_PHILOX])
+        _, _, ww, wh, chunk = self._window_geometry(ZMAX[_lib.RNG_PHILOX], stride=max(1, N // 32))
         self.win_geometry = (ww, wh, chunk)
         pa = _lib.PhotonArgs()
         pa.n_samples, pa.n_bins, pa.chunk_bins = N, W, chunk

@@ -188,7 +188,9 @@ class ExposureGenerator(object):
         if add_non_linear:
             nl = eng.cached_plane(('nl', det.non_linear_file_name, F),
                                   lambda: tuple(eng.to_dev(p) for p in det.non_linear_planes(F)))
-        zero = eng.to_dev(zero_read) if np.any(zero_read) else None
+        zero = None
+        if zero_read is not None:
+            zero = eng.cached_plane(('bias', self.SUBARRAY), lambda: eng.to_dev(zero_read))
         return sky, gain, nl, zero
 
     def _dark_stack(self, R):
@@ -261,7 +263,11 @@ class ExposureGenerator(object):
             'clip_values_det_limits': clip_values_det_limits, 'rng': mode,
         })
         self.exposure = exposure.Exposure(self.detector, self.grism, self.planet, self.exp_info)
-        zero_read, zero_read_info = self._gen_zero_read(add_initial_bias)
+        # the zero read is the initial bias for SUBARRAY 256 and zeros otherwise
+        # (:446-466); the all-zero case never materialises an F x F host array
+        has_bias = bool(self.SUBARRAY == 256 and add_initial_bias)
+        zero_read = self.detector.get_initial_bias() if has_bias else None
+        zero_read_info = {'cumulative_exp_time': 0 * u.s, 'read_exp_time': 0 * u.s, 'CRPIX1': 0}
 
         if progress_bar is not None:
             progress_bar.print_status_line(progress_bar.progress_line + ' (device)')
