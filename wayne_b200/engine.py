@@ -103,11 +103,17 @@ class DeviceEngine(object):
     _TORCH_DT = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
                  np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
 
-    def to_dev_many(self, arrays):
+    def to_dev_many(self, arrays, ahead=False):
         """Several small host arrays -> device tensors with ONE host->device copy:
-        packed (16-byte aligned) into a pinned staging buffer, copied on the
-        current stream, returned as typed views of the device buffer.  A dozen
-        separate pageable copies per exposure cost ~35 us of stream time each."""
+        packed (16-byte aligned) into a pinned staging buffer and returned as
+        typed views of the device buffer.  A dozen separate pageable copies per
+        exposure cost ~35 us of stream time each.
+
+        ahead=True issues the copy on the upload stream (the current stream waits
+        for it): a copy in stream order on the compute stream is only handed to
+        the copy engine when the previous exposure's kernels have finished, by
+        which time the engine is busy with a later exposure's 135 MB upload and
+        the small copy -- and with it the whole exposure -- waits behind it."""
         arrays = [np.ascontiguousarray(a) for a in arrays]
         offs, total = [], 0
         for a in arrays:
@@ -119,7 +125,17 @@ class DeviceEngine(object):
         host = stage.numpy()
         for a, o in zip(arrays, offs):
             host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
-        dev = stage.to(self.device, non_blocking=True)
+        if ahead:
+            _, up = self._streams()
+            cur = torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(up):
+                dev = stage.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+            cur.wait_event(ev)
+            dev.record_stream(cur)
+        else:
+            dev = stage.to(self.device, non_blocking=True)
         out = []
         for a, o in zip(arrays, offs):
             t = dev[o:o + a.nbytes].view(self._TORCH_DT[a.dtype]).reshape(a.shape)
@@ -325,7 +341,7 @@ class ExposureRun(object):
         small += [aux[k] for k in aux_names]
         if not flux_is_dev:
             small.append(np.ascontiguousarray(flux, dtype=np.float64))
-        packed = e.to_dev_many(small)
+        packed = e.to_dev_many(small, ahead=True)
         self.d_wl, self.d_xr, self.d_yr, self.d_dur, self.d_read_end = packed[:5]
         self.aux = dict(zip(aux_names, packed[5:5 + len(aux_names)]))
         self.d_flux = e.to_dev(flux) if flux_is_dev else packed[-1]
