@@ -619,16 +619,21 @@ k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_a
         }
         if (q >= qend)
             continue; // (no collectives below)
+        // flat walk over the run (all lanes execute the same body every trip; a
+        // lane steps to its next bin when the current one has no units left)
         BinPar cur = mybins[b];
-        for (; q < qend; ++q) {
-            int j = q - cur.excl;
-            while (j >= cur.units) { // next bin with units (empty bins have units == 0)
+        int j = q - cur.excl;          // unit index inside the current bin
+        int rem = cur.units - j;       // units of the current bin still to do
+        uint32_t cbin = (uint32_t)(wb + b);
+        for (int n = qend - q; n > 0; --n, ++j, --rem) {
+            while (rem <= 0) {         // next bin with units (empty bins have units == 0)
                 ++b;
+                ++cbin;
                 cur = mybins[b];
-                j = q - cur.excl;
+                j = 0;
+                rem = cur.units;
             }
-            const uint4 r = philox4x32_10_keys(
-                make_uint4((uint32_t)j, (uint32_t)(wb + b), s_glob, WB_STREAM_PHOTONS), keys);
+            const uint4 r = philox4x32_10_keys(make_uint4((uint32_t)j, cbin, s_glob, WB_STREAM_PHOTONS), keys);
             // both electrons of the unit in straight-line code (their MUFU chains
             // interleave); the second is masked off for an odd count's last unit
             const int k0 = 2 * j;
