@@ -423,24 +423,43 @@ def run_native(args, wk):
                    + (R + 1) * F * F * 8)   # NSAMP reads written
     t_reads, t_throw, t_gather, t_counts = per('k_reads'), per('k_throw'), per('k_gather'), per('k_counts')
     ww, wh, chunk = geom
-    gather_bytes = N * ww * wh * 4 + 2 * R * F * F * 8
+    gather_bytes = N * ww * wh * 4 + 2 * R * F * F * 8     # only on the window/gather (parity) path
     roof_hbm = {'kernel': 'k_reads<0>', 'bound': 'hbm', 'achieved': reads_bytes / (t_reads * 1e-3) / 1e9,
                 'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': peak_src,
                 'frac': reads_bytes / (t_reads * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
                 'algorithmic_bytes': reads_bytes, 'ms': t_reads}
-    smem_peak = None
-    try:
-        import ctypes as C
+    # measured denominators for the photon kernel (no memory traffic to speak of):
+    #   mb(7)  Philox4x32-10 + fp32 Box-Muller per electron and nothing else -- the
+    #          issue-slot ceiling of GENERATING electrons on this GPU
+    #   mb(2)  shared-memory atomics with the PSF's 3x3 same-address pattern
+    #   mb(1)  conflict-free shared-memory atomics
+    import ctypes as C
+
+    def microbench(which, iters):
         ms, ops = C.c_double(), C.c_double()
-        _lib.check(_lib.lib.wb200_microbench(0, 4096, C.byref(ms), C.byref(ops)), 'microbench')
-        smem_peak = ops.value / (ms.value * 1e-3) / 1e9
-    except Exception:
+        _lib.check(_lib.lib.wb200_microbench(which, iters, C.byref(ms), C.byref(ops)), 'microbench')
+        return ops.value / (ms.value * 1e-3) / 1e9
+
+    try:
+        rng_peak, atom_psf, atom_free = microbench(7, 2048), microbench(2, 4096), microbench(1, 4096)
+    except Exception:      # noqa: BLE001
+        rng_peak = atom_psf = atom_free = None
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            traffic = json.load(f)
+    except Exception:      # noqa: BLE001
         pass
-    roof_throw = {'kernel': 'k_throw<PHILOX>', 'bound': 'smem_atomic', 'achieved': photons / (t_throw * 1e-3) / 1e9,
-                  'peak': smem_peak, 'unit': 'Gphoton/s (1 shared-memory atomic increment per photon)',
-                  'peak_source': 'wb200_microbench(0): conflict-free shared atomicAdd, all SMs, measured in this run',
-                  'frac': (photons / (t_throw * 1e-3) / 1e9 / smem_peak) if smem_peak else None,
-                  'traffic': None, 'ms': t_throw}
+    roof_hbm['traffic'] = traffic.get('k_reads')
+    roof_hbm['traffic_source'] = traffic.get('source')
+    roof_throw = {'kernel': 'k_throw_philox (direct accumulation)',
+                  'bound': 'sm_issue: Philox4x32-10 + Box-Muller + shared-memory atomic per electron (HBM idle)',
+                  'achieved': photons / (t_throw * 1e-3) / 1e9, 'peak': rng_peak,
+                  'unit': 'Gelectron/s',
+                  'peak_source': 'wb200_microbench(7): Philox4x32-10 + fp32 Box-Muller only, all SMs, this run',
+                  'frac': (photons / (t_throw * 1e-3) / 1e9 / rng_peak) if rng_peak else None,
+                  'smem_atomic_peaks_gops': {'psf_like_3x3': atom_psf, 'conflict_free': atom_free},
+                  'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
     dominant = max(stages.items(), key=lambda kv: kv[1][0])[0]
     line = {
         'metric': 'exposures_per_s', 'value': world * 1e3 / ms_value, 'unit': 'exposures/s',
@@ -450,7 +469,7 @@ def run_native(args, wk):
         'photons_per_s': world * photons * 1e3 / ms_value,
         'config': {'workload': wk['desc'], 'n_subsamples': N, 'n_bins': W, 'rng': 'philox',
                    'out_dtype': 'float64', 'window': [ww, wh], 'chunk_bins': chunk,
-                   'l2': 'no flush: per-exposure working set (windows+planes+reads, > 500 MB) exceeds the 126 MB L2'},
+                   'l2': 'no flush: per-exposure working set (planet signal 135 MB + interval planes 117 MB + dark 235 MB + reads 126 MB) exceeds the 126 MB L2'},
         'clocks': clocks,
         'e2e': {'value': world * 1e3 / ms_e2e, 'unit': 'exposures/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
@@ -464,8 +483,8 @@ def run_native(args, wk):
         'roofline': roof_throw if dominant == 'k_throw' else roof_hbm,
         'roofline_hbm': roof_hbm,
         'roofline_photons': roof_throw,
-        'gather': {'ms': t_gather, 'algorithmic_bytes': gather_bytes,
-                   'achieved_gbs': gather_bytes / (t_gather * 1e-3) / 1e9 if t_gather else None},
+        'gather': ({'ms': t_gather, 'algorithmic_bytes': gather_bytes,
+                    'achieved_gbs': gather_bytes / (t_gather * 1e-3) / 1e9} if t_gather else None),
     }
     if world == 1 and not args.no_cpu:
         sec, info = cpu_reference_exposure(wk, inp, 4 * len(inp['read_index']))
