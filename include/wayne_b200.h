@@ -127,6 +127,33 @@ int wb200_counts(int n_samples, int n_bins, const double *d_flux,
                  double *d_expected, int32_t *d_counts, uint64_t *d_totals,
                  void *stream);
 
+/* Same stage with the planet signal given as a per-sub-sample Chebyshev
+ * expansion in the bin's radius ratio instead of an [n_samples][n_bins] array:
+ *   depth[s][w] = sum_k coef[s][k] T_k(x[w])     (Clenshaw, numpy chebval order)
+ * -- the light curves of Observation.generate_lightcurves (wayne/observation.py:
+ * 293-357, 441-443) evaluated inside the counts kernel, so the 8 bytes per
+ * (sub-sample, bin) planet-signal array is never built or copied.
+ * d_cheb_coef [n_samples][cheb_order], d_cheb_x [n_bins]; cheb_order 1..32.
+ * When d_cheb_coef is NULL, d_depth / depth_ld are used as in wb200_counts. */
+typedef struct wb200_counts_args {
+    int32_t n_samples, n_bins, count_mode, cheb_order;
+    uint32_t key0, key1;
+    double scale;
+    int64_t depth_ld;
+    const double *d_flux;
+    const double *d_depth;
+    const double *d_cheb_coef;
+    const double *d_cheb_x;
+    const double *d_sens;
+    const double *d_dwl;
+    const double *d_dur_ms;
+    double *d_expected;
+    int32_t *d_counts;
+    uint64_t *d_totals;
+} wb200_counts_args;
+
+int wb200_counts_ex(const wb200_counts_args *args, void *stream);
+
 /* Exclusive prefix of counts along bins, per sub-sample (electron offsets of
  * the compat / deterministic modes = the reference's running electron_counter,
  * pyparallel_menu.c:86-107).  d_offsets [n_samples][n_bins] int32. */

@@ -215,3 +215,68 @@ def test_direct_accumulation_equals_window_gather_path(calb_dir, monkeypatch):
                             add_non_linear=False, add_read_noise=False, add_initial_bias=False,
                             rng_key=(7, 7))
     assert np.array_equal(np.array([r[0] for r in exp.reads]), a)
+
+
+def test_stochastic_mode_ks_and_moments_100_seeds(calb_dir):
+    """north_star's stochastic criterion: per pixel, over 100 seeds, the native
+    (Philox) exposures and the reference-stream oracle exposures come from the
+    same distribution -- two-sample KS test per pixel, and mean / variance within
+    3 sigma of their sampling errors."""
+    from scipy import stats
+    from wayne import units as u
+    cal = harness.oracle_calibration()
+    wl, flux, planet = harness.spectrum(level=1.5e-15, n_wl=256)
+    n_seeds = 100
+    G, O_ = [], []
+    for s in range(n_seeds):
+        eg = _gen(rng='philox')
+        _, mid, dur, ri = eg._gen_scanning_sample_times(1 * u.year)
+        exp = eg.scanning_frame(X_REF, Y_REF, 0.01, 0.01, wl * u.micron, flux, None, 0 * u.pixel / u.s,
+                                1 * u.year, mid, dur, ri, cosmic_rate=None,
+                                sky_background=2.0 * u.count / u.s, rng_key=(20170410, s))
+        G.append(exp.reads[-1][0][70:95, 40:230].copy())      # the trace and its wings
+        o = E.scanning_frame(cal, 'G141', 256, eg.read_times.to(u.s).value, wl, flux, None, X_REF, Y_REF,
+                             0.01, 0.01, 0.0, 365.25 * 86400e3, np.random.RandomState(5000 + s),
+                             cosmic_rate=None, sky_background=2.0, threads=1)
+        O_.append(o['reads'][-1][70:95, 40:230])
+    G, O_ = np.array(G), np.array(O_)
+    npix = G[0].size
+    # mean and variance per pixel
+    gm, om = G.mean(0), O_.mean(0)
+    gv, ov = G.var(0, ddof=1), O_.var(0, ddof=1)
+    z_mean = (gm - om) / np.sqrt((gv + ov) / n_seeds)
+    assert np.abs(z_mean).max() < 5.0 and (np.abs(z_mean) > 3).mean() < 0.01 and abs(z_mean.mean()) < 0.15
+    # log variance ratio: sampling error sqrt(2/(n-1)) per estimate (Gaussian-ish pixels)
+    z_var = np.log(gv / ov) / np.sqrt(2 * 2.0 / (n_seeds - 1))
+    assert np.abs(z_var).max() < 5.5 and (np.abs(z_var) > 3).mean() < 0.02 and abs(z_var.mean()) < 0.2
+    # two-sample KS per pixel: p-values must look uniform
+    p = np.array([stats.ks_2samp(G[:, i, j], O_[:, i, j]).pvalue
+                  for i in range(G.shape[1]) for j in range(G.shape[2])])
+    assert p.size == npix
+    assert (p < 0.01).mean() < 0.03 and (p < 1e-4).mean() < 0.002 and p.mean() > 0.40
+
+
+def test_chebyshev_planet_signal_equals_array_signal(calb_dir):
+    """The planet signal as a per-sub-sample Chebyshev expansion evaluated inside
+    k_counts gives the same expected counts (and, with rounding instead of
+    Poisson, the same reads) as the materialised [n_samples][n_wl] array."""
+    from wayne import units as u
+    from wayne_b200 import lightcurve as lc
+    wl, flux, planet = harness.spectrum(level=2.0e-14)
+    eg = _gen(rng='philox')
+    _, mid, dur, ri = eg._gen_scanning_sample_times(250 * u.ms)
+    t = 2456196.28836 - 0.06 + np.asarray(u.value_in(mid, u.ms)) / 86400e3
+    sig = lc.planet_signal(t, planet, [0.800627, -0.757066, 0.897268, -0.384804], 3.524746, 8.81, 0.0,
+                           86.71, 0.0, 2456196.28836)
+    arr = sig.to_array()
+    assert arr.max() > 0.01
+    outs = []
+    for ps in (sig, arr):
+        eg = _gen(rng='philox')
+        exp = eg.scanning_frame(X_REF, Y_REF, 0.02, 0.02, wl * u.micron, flux, ps, 7.4325 * u.pixel / u.s,
+                                250 * u.ms, mid, dur, ri, add_dark=False, cosmic_rate=None,
+                                sky_background=0 * u.count / u.s, add_read_noise=False,
+                                add_stellar_noise=False, rng_key=(3, 4))
+        outs.append((np.array([r[0] for r in exp.reads]), eg.photons))
+    assert outs[0][1] == outs[1][1] > 1e6
+    assert np.array_equal(outs[0][0], outs[1][0])

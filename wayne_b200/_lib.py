@@ -44,6 +44,17 @@ class PhotonArgs(C.Structure):
     ]
 
 
+class CountsArgs(C.Structure):
+    _fields_ = [
+        ("n_samples", c_i32), ("n_bins", c_i32), ("count_mode", c_i32), ("cheb_order", c_i32),
+        ("key0", c_u32), ("key1", c_u32),
+        ("scale", c_double), ("depth_ld", c_i64),
+        ("d_flux", c_void_p), ("d_depth", c_void_p), ("d_cheb_coef", c_void_p), ("d_cheb_x", c_void_p),
+        ("d_sens", c_void_p), ("d_dwl", c_void_p), ("d_dur_ms", c_void_p),
+        ("d_expected", c_void_p), ("d_counts", c_void_p), ("d_totals", c_void_p),
+    ]
+
+
 class GatherArgs(C.Structure):
     _fields_ = [
         ("n_samples", c_i32), ("sample0", c_i32), ("n_reads", c_i32),
@@ -99,6 +110,7 @@ SIGNATURES = {
     "wb200_counts": (c_int, [c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
                              c_void_p, c_double, c_int, c_u32, c_u32, c_void_p, c_void_p,
                              c_void_p, c_void_p]),
+    "wb200_counts_ex": (c_int, [C.POINTER(CountsArgs), c_void_p]),
     "wb200_count_offsets": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "wb200_throw_photons": (c_int, [C.POINTER(PhotonArgs), c_void_p]),
     "wb200_throw_photons_at": (c_int, [C.POINTER(PhotonArgs), c_int, c_void_p]),

@@ -172,16 +172,35 @@ __global__ void k_trace_positions(int N, int W, const double *__restrict__ trace
 // exposure_generator.py:344-348 and :602-628.  grid = (ceil(W/256), N).
 __global__ void __launch_bounds__(256)
 k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict__ depth,
-         long long depth_ld, const double *__restrict__ sens, const double *__restrict__ dwl,
-         const double *__restrict__ dur_ms, double scale, int mode, uint32_t k0, uint32_t k1,
-         double *expected, int *counts, unsigned long long *totals)
+         long long depth_ld, const double *__restrict__ cheb_coef, int cheb_order,
+         const double *__restrict__ cheb_x, const double *__restrict__ sens,
+         const double *__restrict__ dwl, const double *__restrict__ dur_ms, double scale, int mode,
+         uint32_t k0, uint32_t k1, double *expected, int *counts, unsigned long long *totals)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
     long long c = 0;
     if (w < W) {
         double f = flux[w];
-        if (depth)
+        if (cheb_coef) {
+            // Clenshaw recurrence in numpy.polynomial.chebyshev.chebval's order
+            const double *cf = cheb_coef + (size_t)s * cheb_order;
+            const double x = cheb_x[w];
+            double d;
+            if (cheb_order == 1) {
+                d = cf[0];
+            } else {
+                const double x2 = 2 * x;
+                double c0 = cf[cheb_order - 2], c1 = cf[cheb_order - 1];
+                for (int i = 3; i <= cheb_order; ++i) {
+                    const double tmp = c0;
+                    c0 = cf[cheb_order - i] - c1;
+                    c1 = tmp + c1 * x2;
+                }
+                d = c0 + c1 * x;
+            }
+            f = f * (1. - d);
+        } else if (depth)
             f = f * (1. - depth[(size_t)s * depth_ld + w]);
         double e = f * sens[w];  // ph / s / angstrom
         e = e * dwl[w];          // (ph/s/A) * micron

@@ -196,24 +196,50 @@ int wb200_trace_positions(int n_samples, int n_bins, const double *d_trace, cons
     return WB200_OK;
 }
 
+int wb200_counts_ex(const wb200_counts_args *a, void *stream)
+{
+    WB_REQUIRE(a != nullptr, "null args");
+    WB_REQUIRE(a->n_samples > 0 && a->n_samples <= 65535 && a->n_bins > 0, "bad sizes");
+    WB_REQUIRE(a->d_flux && a->d_sens && a->d_dwl && a->d_dur_ms && a->d_totals, "null buffer");
+    WB_REQUIRE(a->count_mode >= 0 && a->count_mode <= 2, "bad count_mode");
+    WB_REQUIRE(a->count_mode == WB200_COUNT_NONE || a->d_counts, "counts output needed");
+    WB_REQUIRE(!a->d_cheb_coef || (a->d_cheb_x && a->cheb_order >= 1 && a->cheb_order <= 32),
+               "Chebyshev planet signal: need x and 1 <= order <= 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    WB_CUDA(cudaMemsetAsync(a->d_totals, 0, sizeof(uint64_t) * a->n_samples, st));
+    dim3 grid((a->n_bins + 255) / 256, a->n_samples);
+    k_counts<<<grid, 256, 0, st>>>(a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld,
+                                   a->d_cheb_coef, a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl,
+                                   a->d_dur_ms, a->scale, a->count_mode, a->key0, a->key1, a->d_expected,
+                                   a->d_counts, (unsigned long long *)a->d_totals);
+    WB_LAUNCHED("k_counts");
+    return WB200_OK;
+}
+
 int wb200_counts(int n_samples, int n_bins, const double *d_flux, const double *d_depth,
                  int64_t depth_ld, const double *d_sens, const double *d_dwl,
                  const double *d_dur_ms, double scale, int count_mode, uint32_t key0,
                  uint32_t key1, double *d_expected, int32_t *d_counts, uint64_t *d_totals,
                  void *stream)
 {
-    WB_REQUIRE(n_samples > 0 && n_samples <= 65535 && n_bins > 0, "bad sizes");
-    WB_REQUIRE(d_flux && d_sens && d_dwl && d_dur_ms && d_totals, "null buffer");
-    WB_REQUIRE(count_mode >= 0 && count_mode <= 2, "bad count_mode");
-    WB_REQUIRE(count_mode == WB200_COUNT_NONE || d_counts, "counts output needed");
-    cudaStream_t st = (cudaStream_t)stream;
-    WB_CUDA(cudaMemsetAsync(d_totals, 0, sizeof(uint64_t) * n_samples, st));
-    dim3 grid((n_bins + 255) / 256, n_samples);
-    k_counts<<<grid, 256, 0, st>>>(n_samples, n_bins, d_flux, d_depth, (long long)depth_ld, d_sens,
-                                   d_dwl, d_dur_ms, scale, count_mode, key0, key1, d_expected,
-                                   d_counts, (unsigned long long *)d_totals);
-    WB_LAUNCHED("k_counts");
-    return WB200_OK;
+    wb200_counts_args a;
+    memset(&a, 0, sizeof(a));
+    a.n_samples = n_samples;
+    a.n_bins = n_bins;
+    a.count_mode = count_mode;
+    a.key0 = key0;
+    a.key1 = key1;
+    a.scale = scale;
+    a.depth_ld = depth_ld;
+    a.d_flux = d_flux;
+    a.d_depth = d_depth;
+    a.d_sens = d_sens;
+    a.d_dwl = d_dwl;
+    a.d_dur_ms = d_dur_ms;
+    a.d_expected = d_expected;
+    a.d_counts = d_counts;
+    a.d_totals = d_totals;
+    return wb200_counts_ex(&a, stream);
 }
 
 int wb200_count_offsets(int n_samples, int n_bins, const int32_t *d_counts, int32_t *d_offsets,

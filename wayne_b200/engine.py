@@ -333,10 +333,21 @@ class ExposureRun(object):
 
         e = engine
         st = e.stream_ptr()
+        self.cheb_order = 0
+        cheb = depth if hasattr(depth, 'coef') and hasattr(depth, 'x') else None
+        if cheb is not None:
+            # planet signal as a per-sub-sample Chebyshev expansion (lightcurve.ChebyshevSignal):
+            # evaluated inside k_counts, never materialised
+            depth = None
+            self.cheb_order = int(cheb.coef.shape[1])
+            self._cheb_host = (np.ascontiguousarray(cheb.coef[:self.N], dtype=np.float64),
+                               np.ascontiguousarray(cheb.x[depth_col0:depth_col0 + self.W], dtype=np.float64))
         flux_is_dev = isinstance(flux, torch.Tensor)
         small = [self.wl_host, self.xr_host, self.yr_host, np.ascontiguousarray(dur_ms, dtype=np.float64),
                  self.read_end_host]
         aux = dict(aux or {})
+        if self.cheb_order:
+            aux['_cheb_coef'], aux['_cheb_x'] = self._cheb_host
         aux_names = sorted(aux)
         small += [aux[k] for k in aux_names]
         if not flux_is_dev:
@@ -425,6 +436,23 @@ class ExposureRun(object):
               "wb200_trace_positions")
         return xp.cpu().numpy(), yp.cpu().numpy()
 
+    def _counts_args(self, mode, key, d_expected, d_counts):
+        a = _lib.CountsArgs()
+        a.n_samples, a.n_bins, a.count_mode, a.cheb_order = self.N, self.W, mode, self.cheb_order
+        a.key0, a.key1 = key[0] & 0xffffffff, key[1] & 0xffffffff
+        a.scale, a.depth_ld = self.scale, self.depth_ld
+        a.d_flux = self.d_flux.data_ptr()
+        a.d_depth = self.depth_ptr
+        if self.cheb_order:
+            a.d_cheb_coef = self.aux['_cheb_coef'].data_ptr()
+            a.d_cheb_x = self.aux['_cheb_x'].data_ptr()
+        a.d_sens, a.d_dwl, a.d_dur_ms = (self.d_sens.data_ptr(), self.d_dwl.data_ptr(),
+                                         self.d_dur.data_ptr())
+        a.d_expected = d_expected.data_ptr() if d_expected is not None else None
+        a.d_counts = d_counts.data_ptr() if d_counts is not None else None
+        a.d_totals = self.d_totals.data_ptr()
+        return a
+
     # ------------------------------------------------------------------
     def counts(self, mode, key=(0, 0), counts=None, want_expected=False):
         """Stage 1c: expected electrons and their integer draw.
@@ -444,12 +472,8 @@ class ExposureRun(object):
         else:
             self.d_counts = e.empty((self.N, self.W), torch.int32)
         e.mark('k_counts', True)
-        check(lib.wb200_counts(self.N, self.W, _ptr(self.d_flux), self.depth_ptr, self.depth_ld,
-                               _ptr(self.d_sens), _ptr(self.d_dwl), _ptr(self.d_dur), self.scale,
-                               mode, key[0] & 0xffffffff, key[1] & 0xffffffff,
-                               _ptr(self.d_expected) if want_expected else None,
-                               _ptr(self.d_counts), _ptr(self.d_totals), e.stream_ptr()),
-              "wb200_counts")
+        a = self._counts_args(mode, key, self.d_expected if want_expected else None, self.d_counts)
+        check(lib.wb200_counts_ex(C.byref(a), e.stream_ptr()), "wb200_counts")
         e.mark('k_counts', False)
         self._release_depth()
 
@@ -459,11 +483,8 @@ class ExposureRun(object):
                 raise RuntimeError("the planet-signal buffer of this exposure has been recycled; "
                                    "call counts(..., want_expected=True) to keep the expected counts")
             self.d_expected = self.e.empty((self.N, self.W))
-            check(lib.wb200_counts(self.N, self.W, _ptr(self.d_flux), self.depth_ptr,
-                                   self.depth_ld, _ptr(self.d_sens), _ptr(self.d_dwl),
-                                   _ptr(self.d_dur), self.scale, _lib.COUNT_NONE, 0, 0,
-                                   _ptr(self.d_expected), None, _ptr(self.d_totals),
-                                   self.e.stream_ptr()), "wb200_counts")
+            a = self._counts_args(_lib.COUNT_NONE, (0, 0), self.d_expected, None)
+            check(lib.wb200_counts_ex(C.byref(a), self.e.stream_ptr()), "wb200_counts")
         return self.d_expected.cpu().numpy()
 
     # ------------------------------------------------------------------

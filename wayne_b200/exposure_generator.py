@@ -308,7 +308,10 @@ class ExposureGenerator(object):
         flux = np.asarray(getattr(stellar_flux, 'value', stellar_flux), dtype=np.float64)[i0:i1]
         depth = None
         if planet_signal is not None:
-            depth = planet_signal if hasattr(planet_signal, 'is_cuda') else np.asarray(planet_signal)
+            if hasattr(planet_signal, 'is_cuda') or hasattr(planet_signal, 'coef'):
+                depth = planet_signal          # CUDA tensor, or lightcurve.ChebyshevSignal
+            else:
+                depth = np.asarray(planet_signal)
             if depth.ndim != 2 or depth.shape[0] < num_samples:
                 raise ValueError("planet_signal must be [n_samples][n_wl]")
             depth = depth[:num_samples]

@@ -89,3 +89,72 @@ def crop_central_box(array, size):
         return array
     i = (n - size) // 2
     return array[i:n - i, i:n - i]
+
+
+# ---------------------------------------------------------------------------
+# spectrum preparation for the visit driver (upstream of the
+# exposure path, host-side, once per visit)
+# ---------------------------------------------------------------------------
+def load_and_sort_spectrum(file_path):
+    """Two whitespace-separated columns (wl, flux or depth), sorted by wl
+    (wayne/tools.py:172-186)."""
+    data = np.loadtxt(file_path, dtype=np.float64, ndmin=2)
+    order = np.argsort(data[:, 0], kind='stable')
+    return data[order, 0], data[order, 1]
+
+
+def order_flux_grid(wavelength, spectrum):
+    order = np.argsort(np.asarray(wavelength), kind='stable')
+    return np.asarray(wavelength, dtype=float)[order], np.asarray(spectrum, dtype=float)[order]
+
+
+def load_pheonix_stellar_grid_fits(fits_file):
+    """PHOENIX model table (columns Wavelength, Flux), sorted, duplicate
+    wavelengths removed (wayne/tools.py:152-170; spelling kept)."""
+    from . import fitsio
+    with fitsio.open(fits_file) as f:
+        tab = f[1].data
+        wl, flux = order_flux_grid(tab['Wavelength'], tab['Flux'])
+    keep = np.nonzero(np.diff(wl))
+    return wl[keep], flux[keep]
+
+
+def wl_at_resolution(R, wl_min, wl_max):
+    """Evenly spaced grid with spacing (mid wavelength) / R (wayne/tools.py:303-314)."""
+    mid_wl = (wl_max - wl_min) / 2 + wl_min
+    delta_wl = mid_wl / R
+    return np.arange(wl_min, wl_max + delta_wl, delta_wl)
+
+
+def rebin_spec(wavelength, spectrum, new_wavelength):
+    """Flux-conserving rebinning onto the bins centred on ``new_wavelength``.
+
+    The reference delegates to pysynphot (wayne/tools.py:131-149), which is not
+    available; this is the same definition -- the mean of the piecewise-linear
+    input spectrum over each output bin (bin edges half-way between centres) --
+    written out: the cumulative trapezoid integral of the input is interpolated
+    at the bin edges and differenced."""
+    wl = np.asarray(wavelength, dtype=float)
+    sp = np.asarray(spectrum, dtype=float)
+    new = np.asarray(new_wavelength, dtype=float)
+    edges = bin_centers_to_edges(new)
+    cum = np.concatenate([[0.0], np.cumsum(0.5 * (sp[1:] + sp[:-1]) * np.diff(wl))])
+    # integral up to an arbitrary x: cum at the left node + trapezoid of the partial segment
+    xe = np.clip(edges, wl[0], wl[-1])
+    k = np.clip(np.searchsorted(wl, xe, side='right') - 1, 0, len(wl) - 2)
+    dx = xe - wl[k]
+    slope = (sp[k + 1] - sp[k]) / (wl[k + 1] - wl[k])
+    integ = cum[k] + sp[k] * dx + 0.5 * slope * dx * dx
+    width = np.diff(xe)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        out = np.where(width > 0, np.diff(integ) / width, 0.0)
+    return out
+
+
+def blackbody_lambda(wl_micron, temperature):
+    """Planck B_lambda [erg / (s cm^2 angstrom sr)] at wl [micron] (stands in for
+    astropy's blackbody_lambda, wayne/run_visit.py:203)."""
+    h, c, k = 6.62607015e-27, 2.99792458e10, 1.380649e-16
+    lam = np.asarray(wl_micron, dtype=float) * 1e-4            # cm
+    b = 2 * h * c * c / lam ** 5 / np.expm1(h * c / (lam * k * temperature))   # per cm
+    return b * 1e-8                                            # per angstrom
