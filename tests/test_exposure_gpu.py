@@ -265,7 +265,7 @@ def test_chebyshev_planet_signal_equals_array_signal(calb_dir):
     wl, flux, planet = harness.spectrum(level=2.0e-14)
     eg = _gen(rng='philox')
     _, mid, dur, ri = eg._gen_scanning_sample_times(250 * u.ms)
-    t = 2456196.28836 - 0.06 + np.asarray(u.value_in(mid, u.ms)) / 86400e3
+    t = 2456196.28836 - 0.0002 + np.asarray(u.value_in(mid, u.ms)) / 86400e3
     sig = lc.planet_signal(t, planet, [0.800627, -0.757066, 0.897268, -0.384804], 3.524746, 8.81, 0.0,
                            86.71, 0.0, 2456196.28836)
     arr = sig.to_array()
