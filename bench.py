@@ -271,6 +271,8 @@ def run_native(args, wk):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from wayne_b200.engine import bind_to_gpu_numa_node
+    numa_bound = bind_to_gpu_numa_node(local) if world > 1 else False
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     calibration_dir(wk)
@@ -476,7 +478,7 @@ def run_native(args, wk):
                 'host_issue_ms': [round(float(np.median(t_issue)), 3), round(float(np.max(t_issue)), 3)],
                 'host_wait_ms': [round(float(np.median(t_wait)), 3), round(float(np.max(t_wait)), 3)],
                 'host_step_ms': [round(a_ + b_, 2) for a_, b_ in zip(t_issue, t_wait)]},
-        'gpu_launches': int(launches),
+        'gpu_launches': int(launches), 'numa_bound': bool(numa_bound),
         'host_issue_ms': [round(float(np.median(v_issue)), 3), round(float(np.max(v_issue)), 3)],
         'stage_ms': {k: v[0] / args.steps for k, v in stages.items()},
         'dominant_kernel': dominant,

@@ -46,6 +46,25 @@ def _dp(a):
     return a.ctypes.data_as(_lib.DP)
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs closest to its GPU (NVML's ideal CPU
+    affinity), so pinned host buffers are first-touched on the GPU's NUMA node
+    and per-rank copies do not cross sockets.  Best effort: returns False when
+    NVML is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = device_index
+        if vis and vis.split(',')[device_index].strip().isdigit():
+            phys = int(vis.split(',')[device_index])
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:      # noqa: BLE001
+        return False
+
+
 def tune_host():
     """Call once after start-up in a long-running driver: moves every object alive
     now into the garbage collector's permanent generation (gc.freeze), so the

@@ -149,7 +149,11 @@ def run(argv=None):
     import torch
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     if torch.cuda.is_available():
-        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        if world > 1:
+            from .engine import bind_to_gpu_numa_node
+            bind_to_gpu_numa_node(local)
     out = obs.run_observation(shard=(rank, world))
     sys.stdout.write('rank {}: wrote {} exposures to {}\n'.format(rank, len(out), obs.outdir))
     return out
