@@ -10,13 +10,21 @@ expressions round through float32 (noted where they do).  The electron thrower
 is NOT restated here: it is oracle/psf.py (C restatement, pinned bit-for-bit to
 the unmodified reference kernel).
 
-Pinning: the reference's own tests hold KATs only for the trace / dispersion
-math, bin widths, read times and the visit trend (tests/test_grism.py,
-test_tools.py, test_detector.py, test_visit_trends.py) -- tests/test_oracle_kats.py
-checks this module against every one of them.  Nothing in the reference pins
-_gen_subsample, the flat, the read reductions or the post-exposure chain
-("parity unpinned" for those; the restatement + the compiled reference kernel
-is the pin we define).
+Pinning:
+ (1) every KAT the reference's own tests hold for the path (trace / dispersion,
+     bin widths, read times, visit trend: tests/test_grism.py, test_tools.py,
+     test_detector.py, test_visit_trends.py) -- tests/test_oracle_kats.py;
+ (2) golden vectors produced by EXECUTING the reference's own function bodies
+     under Python 3 (ast extraction from /root/reference + Python-2 division
+     shim; tests/golden/make_reference_goldens.py -> reference_goldens.npz):
+     _SpectrumTrace / wavelength_calibration_coeffs, G141.get_flat_field (bit
+     for bit, float32 storage included), WFC3_IR.apply_non_linearity (bit for
+     bit), tools helpers, MinMaxPossionCosmicGenerator draw order, SSVSine,
+     HookAndLongTermRamp, _gen_scanning_sample_times -- tests/test_reference_goldens.py.
+ Not executable here and therefore pinned only by this restatement ("parity
+ unpinned"): the astropy unit algebra of _gen_subsample / _flux_to_counts, the
+ order of operations of _add_read_reductions and _post_exposure_reductions
+ (their numpy-1.14 casting is written out explicitly below).
 
 numpy version note: the reference pins numpy 1.14 (README.md:26), i.e. legacy
 value-based casting.  Where that changes an expression's working precision it
@@ -262,6 +270,30 @@ def reset_reference_pixels(a):
     return a
 
 
+def cosmic_frame(rs, rate, time, size, min_count=10000, max_count=35000):
+    """MinMaxPossionCosmicGenerator(rate).cosmic_frame(time, size)
+    (cosmic_rays.py:33-44, 70-139): Poisson number of hits at rate/1024^2 per
+    pixel per second, uniform integer energies, uniform positions (rows first)."""
+    n_hits = rs.poisson(rate / (1024. * 1024.) * (size * size) * time)
+    energies = rs.randint(min_count, max_count, n_hits)
+    rows = rs.randint(0, size, n_hits)
+    cols = rs.randint(0, size, n_hits)
+    frame = np.zeros((size, size))
+    for k in range(n_hits):
+        frame[rows[k], cols[k]] += energies[k]
+    return frame
+
+
+def gen_orbit_start_times_per_exp(time_array, obs_start_index):
+    """visit_trends.py:60-73."""
+    t = np.asarray(time_array, dtype=float)
+    idx = list(obs_start_index) + [len(t)]
+    t0 = np.zeros(len(t))
+    for a, b in zip(idx[:-1], idx[1:]):
+        t0[a:b] = t[a]
+    return t0
+
+
 class Draws(object):
     """(unused placeholder) Source of the numpy-side random numbers, in the reference's order (A.7).
     Default: a legacy RandomState (the reference uses the global one)."""
@@ -354,14 +386,8 @@ def scanning_frame(cal, grism, subarray, read_times_s, wl_um, stellar_flux, plan
                 px = px + rs.normal(noise_mean * dt, noise_std * dt, (L, L))
             if sky_background:                                   # :488-495
                 px = px + rs.poisson(master_sky_scaled(cal, L, sky_background * dt))
-            if cosmic_rate is not None:                          # :498-505, cosmic_rays.py:88-139
-                n_hits = rs.poisson(cosmic_rate / (1024. * 1024.) * (L * L) * dt)
-                energies = rs.randint(10000, 35000, n_hits)
-                rows = rs.randint(0, L, n_hits)
-                cols = rs.randint(0, L, n_hits)
-                px = px.copy()
-                for k in range(n_hits):
-                    px[rows[k], cols[k]] += energies[k]
+            if cosmic_rate is not None:                          # :498-505
+                px = px + cosmic_frame(rs, cosmic_rate, dt, L)
             if add_gain_variations:                              # :507-511
                 px = px / gain_plane(cal, S)
             else:
