@@ -4,24 +4,32 @@
 // 16 B/electron normal table, and its SERIAL scatter loop, for all sub-samples
 // of an exposure in one launch.
 //
-// Mapping to B200
+// Two kernels
+//   k_throw<MODE>        generic / parity kernel: RANDR (the reference's rand_r
+//                        streams reproduced per electron, fp64) and HOST (caller's
+//                        normal table) -- bit-exact against pyparallel_menu.c --
+//                        plus a baseline PHILOX path kept as an A/B reference
+//                        (WB200_GENERIC_THROW=1).
+//   k_throw_philox<DIRECT>  the native kernel (further down): instruction-tuned
+//                        Philox thrower; with DIRECT the flat field and the
+//                        accumulation into the read-interval planes are fused
+//                        into the tile flush.
+//
+// Mapping to B200 (both kernels)
 //   grid  = (bin chunks, sub-samples): thousands of CTAs over 148 SMs.
 //   CTA   = 256 threads, a TH x TW int32 histogram tile in shared memory placed
 //           on the footprint of its bin chunk (trace segment +- ~4 sigma_h).
 //   warp  = takes 32 consecutive bins; a warp-level prefix sum of their work
 //           units turns the ragged "counts[bin] electrons per bin" loop into a
-//           dense stream of units, one per lane (load balance is exact
-//           whatever the counts are); the unit -> bin lookup is a 5-step
-//           shuffle binary search, bin parameters are fetched by shuffle.
+//           dense stream of units (load balance is exact whatever the counts).
 //   unit  = PHILOX: one Philox4x32-10 call = 2 electrons of one bin
 //           RANDR / HOST: one electron (fp64, bit-compatible with the reference)
-//   bin   = shared-memory atomicAdd into the tile; electrons that leave the
-//           tile but not the frame go straight to the HBM window with a global
-//           reduction (rare: |z| > ~4).  At the end the tile is flushed to the
-//           sub-sample's HBM window with integer `red.global.add` -- integer
-//           adds commute, so the histogram is deterministic.
-//   HBM traffic per electron is ~0 by construction; the stage is bound by
-//   shared-memory atomics and SFU/ALU work (roofline).
+//   bin   = shared-memory atomic add into the tile; electrons that leave the
+//           tile but not the frame go straight to HBM (rare: |z| > ~4).  At the
+//           end the tile is flushed with integer atomics -- integer adds
+//           commute, so the result is deterministic.
+//   HBM traffic per electron is ~0 by construction; the stage is bound by issue
+//   slots for RNG + Box-Muller (measured: profiles/), not by the atomics.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"

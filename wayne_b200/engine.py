@@ -14,11 +14,15 @@ compat mode, units) lives in exposure_generator.py; this module is mechanism.
 HBM layout (all row-major, float64 unless noted)
   tables     wl, ratio, sigl, sigh, sens, dwl           [W]
   trace      {x_ref,y_ref,m_t,c_t,m_w,c_w,m_wl,c_wl}    [N][8]
+  depth      planet signal (array form only)            [N][ld], ring of upload buffers
   counts     int32                                      [N][W]
-  windows    int32, one per sub-sample of a batch       [nb][WH][WW]
-  acc        electrons per read interval, bordered      [R][F][F]
-  planes     sky, gain, zero, nl[7], dark/err[R]        [F][F] each (bordered)
-  out        the NSAMP reads                            [R+1][F][F]
+  acc        electrons per read interval, bordered      [R][F][F]  int64 2^-24 fixed point
+                                                        (native) / float64 (parity path)
+  windows    int32, parity path only                    [nb][WH][WW] one per sub-sample
+  planes     sky, gain, zero, nl[7], dark/err[R]        [F][F] each (bordered), resident
+  out        the NSAMP reads                            [R+1][F][F] -> pooled pinned host memory
+
+Streams: compute (torch's current stream), upload, download; see DESIGN.md 6b.
 """
 from __future__ import annotations
 
