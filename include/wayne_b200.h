@@ -154,6 +154,20 @@ typedef struct wb200_counts_args {
 
 int wb200_counts_ex(const wb200_counts_args *args, void *stream);
 
+/* Light curves on the device: the Chebyshev planet-signal
+ * coefficients wb200_counts_ex consumes, from the projected star-planet
+ * separations of the sub-samples.  Replaces the per-wavelength pylightcurve calls
+ * of Observation.generate_lightcurves (wayne/observation.py:293-357).
+ *   depth(s, p) = 1 - F(z[s], p): Claret four-coefficient limb darkening, occulted
+ *   intensity by Gauss-Legendre quadrature over stellar annuli (n_gl nodes,
+ *   d_gl_x / d_gl_w on [-1, 1]), evaluated at the `order` Chebyshev nodes of the
+ *   radius-ratio interval [p_min, p_max], then transformed to coefficients.
+ * d_z [n_samples] (use a value >= 1 + p_max, e.g. 1e30, when the planet is behind
+ * the star or out of transit); ld4 HOST array; d_coef [n_samples][order] out. */
+int wb200_transit_cheb(int n_samples, int order, const double *d_z, double p_min, double p_max,
+                       const double *ld4, int n_gl, const double *d_gl_x, const double *d_gl_w,
+                       double *d_coef, void *stream);
+
 /* Exclusive prefix of counts along bins, per sub-sample (electron offsets of
  * the compat / deterministic modes = the reference's running electron_counter,
  * pyparallel_menu.c:86-107).  d_offsets [n_samples][n_bins] int32. */

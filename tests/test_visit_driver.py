@@ -115,3 +115,23 @@ def test_short_visit_on_gpu(tmp_path, calb_dir):
     assert sorted(a) == [2, 4] and params.seed == 1963
     g = fitsio.open(os.path.join(outdir, '0002_raw.fits'))
     assert np.array_equal(a[2].reads[-1][0], g[1].data)
+
+
+@pytest.mark.gpu
+def test_device_transit_kernel_matches_host_model():
+    from wayne_b200 import lightcurve as lc
+    from wayne_b200.engine import DeviceEngine
+    orb = dict(period=3.524746, a=8.81, e=0.0, inc_deg=86.71, w_deg=0.0, t0=2456196.28836)
+    depth = 0.0146 * (1 + 0.02 * np.sin(np.linspace(0, 9, 500)))
+    for t in (orb['t0'] + np.linspace(-0.09, 0.09, 333),          # whole transit incl. contacts
+              orb['t0'] + 1.2 + np.linspace(0, 0.01, 17)):        # out of transit
+        host = lc.planet_signal(t, depth, LD, **orb)
+        dev = lc.planet_signal_device(DeviceEngine.get(), t, depth, LD, **orb)
+        assert hasattr(dev.coef, 'is_cuda')
+        npt = np.abs(dev.coef.cpu().numpy() - host.coef).max()
+        assert npt < 1e-13, npt
+        assert np.abs(dev.to_array() - host.to_array()).max() < 1e-13
+    e = dict(orb, e=0.2, w_deg=60.0)
+    t = orb['t0'] + np.linspace(-0.1, 0.1, 101)
+    assert np.abs(lc.planet_signal_device(DeviceEngine.get(), t, depth, LD, **e).to_array()
+                  - lc.planet_signal(t, depth, LD, **e).to_array()).max() < 1e-13

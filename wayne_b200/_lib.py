@@ -111,6 +111,8 @@ SIGNATURES = {
                              c_void_p, c_double, c_int, c_u32, c_u32, c_void_p, c_void_p,
                              c_void_p, c_void_p]),
     "wb200_counts_ex": (c_int, [C.POINTER(CountsArgs), c_void_p]),
+    "wb200_transit_cheb": (c_int, [c_int, c_int, c_void_p, c_double, c_double, DP, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
     "wb200_count_offsets": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "wb200_throw_photons": (c_int, [C.POINTER(PhotonArgs), c_void_p]),
     "wb200_throw_photons_at": (c_int, [C.POINTER(PhotonArgs), c_int, c_void_p]),

@@ -239,6 +239,68 @@ k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------
+// Transit light curves (wayne_b200/lightcurve.py::planet_signal on the device).
+// One CTA per sub-sample, one thread per Chebyshev node of the radius ratio:
+// 1 - flux by Gauss-Legendre quadrature over the occulted annuli, then the
+// discrete Chebyshev transform of the CTA's `order` node values.
+// ---------------------------------------------------------------------------
+struct Claret4 {
+    double c[4];
+};
+
+__device__ __forceinline__ double claret_intensity(double r, const Claret4 &k)
+{
+    const double mu = sqrt(fmax(1.0 - r * r, 0.0));
+    const double sq = sqrt(mu);
+    return 1.0 - k.c[0] * (1.0 - sq) - k.c[1] * (1.0 - mu) - k.c[2] * (1.0 - mu * sq) -
+           k.c[3] * (1.0 - mu * mu);
+}
+
+__global__ void __launch_bounds__(32)
+k_transit_cheb(int N, int order, const double *__restrict__ zs, double pmin, double pmax, Claret4 ld,
+               double total, int n_gl, const double *__restrict__ glx, const double *__restrict__ glw,
+               double *coef)
+{
+    __shared__ double f[32];
+    const int s = blockIdx.x, k = threadIdx.x;
+    const double PI = 3.141592653589793;
+    if (k < order) {
+        const double xk = cos(PI * (k + 0.5) / order);
+        const double p = 0.5 * (pmax - pmin) * xk + 0.5 * (pmax + pmin);
+        const double z = zs[s];
+        double blocked = 0.0;
+        if (z < 1.0 + p && p > 0.0) {
+            const double lo = fmin(fmax(z - p, 0.0), 1.0), hi = fmin(fmax(z + p, 0.0), 1.0);
+            const double span = hi - lo;
+            for (int i = 0; i < n_gl; ++i) {
+                const double sv = 0.5 * (glx[i] + 1.0), w = 0.5 * glw[i];
+                const double r = hi - span * sv * sv; // limb-side square-root behaviour at sv -> 0
+                const double jac = 2.0 * span * sv;
+                double ang;
+                if (z == 0.0)
+                    ang = (r <= p) ? PI : 0.0;
+                else if (r <= p - z)
+                    ang = PI;
+                else
+                    ang = acos(fmin(fmax((r * r + z * z - p * p) / (2.0 * r * z), -1.0), 1.0));
+                blocked += w * jac * claret_intensity(r, ld) * 2.0 * r * ang;
+            }
+        }
+        f[k] = blocked / total; // = 1 - flux
+    }
+    __syncthreads();
+    if (k < order) {
+        double c = 0.0;
+        for (int j = 0; j < order; ++j)
+            c += f[j] * cos(PI * k * (j + 0.5) / order);
+        c *= 2.0 / order;
+        if (k == 0)
+            c *= 0.5;
+        coef[(size_t)s * order + k] = c;
+    }
+}
+
 // Exclusive prefix of counts along bins; one CTA (256 threads) per sub-sample.
 __global__ void __launch_bounds__(256)
 k_count_offsets(int W, const int *__restrict__ counts, int *offsets)

@@ -242,6 +242,25 @@ int wb200_counts(int n_samples, int n_bins, const double *d_flux, const double *
     return wb200_counts_ex(&a, stream);
 }
 
+int wb200_transit_cheb(int n_samples, int order, const double *d_z, double p_min, double p_max,
+                       const double *ld4, int n_gl, const double *d_gl_x, const double *d_gl_w,
+                       double *d_coef, void *stream)
+{
+    WB_REQUIRE(n_samples > 0 && order >= 1 && order <= 32, "1 <= order <= 32");
+    WB_REQUIRE(d_z && ld4 && d_gl_x && d_gl_w && d_coef && n_gl >= 2, "null buffer");
+    WB_REQUIRE(p_max >= p_min && p_min >= 0.0, "bad radius-ratio interval");
+    Claret4 ld;
+    memcpy(ld.c, ld4, sizeof(ld.c));
+    double total = 1.0; // int_0^1 I(r) 2 pi r dr, with int mu^(n/2) 2 r dr = 4/(n+4)
+    for (int n = 1; n <= 4; ++n)
+        total -= ld.c[n - 1] * (1.0 - 4.0 / (n + 4));
+    total *= 3.141592653589793;
+    k_transit_cheb<<<n_samples, 32, 0, (cudaStream_t)stream>>>(n_samples, order, d_z, p_min, p_max, ld,
+                                                               total, n_gl, d_gl_x, d_gl_w, d_coef);
+    WB_LAUNCHED("k_transit_cheb");
+    return WB200_OK;
+}
+
 int wb200_count_offsets(int n_samples, int n_bins, const int32_t *d_counts, int32_t *d_offsets,
                         void *stream)
 {

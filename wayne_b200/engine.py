@@ -363,14 +363,19 @@ class ExposureRun(object):
             # evaluated inside k_counts, never materialised
             depth = None
             self.cheb_order = int(cheb.coef.shape[1])
-            self._cheb_host = (np.ascontiguousarray(cheb.coef[:self.N], dtype=np.float64),
+            coef = cheb.coef[:self.N]
+            self._cheb_dev = coef.contiguous() if isinstance(coef, torch.Tensor) else None
+            self._cheb_host = (None if self._cheb_dev is not None
+                               else np.ascontiguousarray(coef, dtype=np.float64),
                                np.ascontiguousarray(cheb.x[depth_col0:depth_col0 + self.W], dtype=np.float64))
         flux_is_dev = isinstance(flux, torch.Tensor)
         small = [self.wl_host, self.xr_host, self.yr_host, np.ascontiguousarray(dur_ms, dtype=np.float64),
                  self.read_end_host]
         aux = dict(aux or {})
         if self.cheb_order:
-            aux['_cheb_coef'], aux['_cheb_x'] = self._cheb_host
+            aux['_cheb_x'] = self._cheb_host[1]
+            if self._cheb_dev is None:
+                aux['_cheb_coef'] = self._cheb_host[0]
         aux_names = sorted(aux)
         small += [aux[k] for k in aux_names]
         if not flux_is_dev:
@@ -378,6 +383,8 @@ class ExposureRun(object):
         packed = e.to_dev_many(small, ahead=True)
         self.d_wl, self.d_xr, self.d_yr, self.d_dur, self.d_read_end = packed[:5]
         self.aux = dict(zip(aux_names, packed[5:5 + len(aux_names)]))
+        if self.cheb_order and self._cheb_dev is not None:
+            self.aux['_cheb_coef'] = self._cheb_dev
         self.d_flux = e.to_dev(flux) if flux_is_dev else packed[-1]
         if depth is not None:
             if not isinstance(depth, torch.Tensor):

@@ -134,6 +134,33 @@ def eclipse(fp_over_fs, rp, period, a, e, inc_deg, w_deg, t0, t):
     return (1 + fp_over_fs * vis) / (1 + fp_over_fs)
 
 
+def planet_signal_device(engine, t, depth_spectrum, ldcoeffs, period, a, e, inc_deg, w_deg, t0, order=8,
+                         nodes=96):
+    """:func:`planet_signal` with the quadrature on the GPU (wb200_transit_cheb):
+    the coefficients stay in HBM and go straight into k_counts.  The host only
+    solves Kepler's equation for the sub-sample times."""
+    import ctypes as C
+
+    from . import _lib
+    rp = np.sqrt(np.asarray(depth_spectrum, dtype=np.float64))
+    pmin, pmax = float(rp.min()), float(rp.max())
+    if pmax - pmin < 1e-12:
+        pmax = pmin + 1e-12
+    z, front = kepler_separation(t, period, a, e, inc_deg, w_deg, t0)
+    z = np.where(front, z, 1e30)
+    glx, glw = engine.cached_plane(('gauss_legendre', nodes),
+                                   lambda: engine.to_dev_many(list(_gauss_legendre(nodes))))
+    d_z, = engine.to_dev_many([z], ahead=True)
+    coef = engine.empty((len(z), order))
+    ld = np.ascontiguousarray(ldcoeffs, dtype=np.float64)
+    _lib.check(_lib.lib.wb200_transit_cheb(len(z), order, C.c_void_p(d_z.data_ptr()), pmin, pmax,
+                                           ld.ctypes.data_as(_lib.DP), nodes, C.c_void_p(glx.data_ptr()),
+                                           C.c_void_p(glw.data_ptr()), C.c_void_p(coef.data_ptr()),
+                                           engine.stream_ptr()), "wb200_transit_cheb")
+    x = (2 * rp - (pmax + pmin)) / (pmax - pmin)
+    return ChebyshevSignal(coef, x)
+
+
 class ChebyshevSignal(object):
     """Planet signal (1 - relative flux) of an exposure as a per-sub-sample
     Chebyshev expansion in the radius ratio:  depth[s][w] = sum_k coef[s][k] T_k(x[w]),
@@ -144,17 +171,21 @@ class ChebyshevSignal(object):
     ndim = 2
 
     def __init__(self, coef, x):
-        self.coef = np.ascontiguousarray(coef, dtype=np.float64)
+        # coef may be a CUDA tensor (planet_signal_device): it then never leaves HBM
+        self.coef = coef if hasattr(coef, 'is_cuda') else np.ascontiguousarray(coef, dtype=np.float64)
         self.x = np.ascontiguousarray(x, dtype=np.float64)
         self.shape = (self.coef.shape[0], self.x.shape[0])
+
+    def _host_coef(self):
+        return self.coef.cpu().numpy() if hasattr(self.coef, 'is_cuda') else self.coef
 
     def __getitem__(self, item):
         if isinstance(item, slice):
             return ChebyshevSignal(self.coef[item], self.x)
-        return np.polynomial.chebyshev.chebval(self.x, self.coef[item])
+        return np.polynomial.chebyshev.chebval(self.x, self._host_coef()[item])
 
     def to_array(self):
-        return np.polynomial.chebyshev.chebval(self.x, self.coef.T)
+        return np.polynomial.chebyshev.chebval(self.x, self._host_coef().T)
 
 
 def planet_signal(t, depth_spectrum, ldcoeffs, period, a, e, inc_deg, w_deg, t0, order=8, nodes=96):

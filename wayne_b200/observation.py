@@ -184,8 +184,16 @@ class Observation(object):
             models[:, j] = m
         return models
 
-    def _planet_signal(self, time_array):
+    def _planet_signal(self, time_array, device=True):
+        """Chebyshev planet signal of one exposure's sub-sample times; with a CUDA
+        device the quadrature runs on the GPU (wb200_transit_cheb)."""
         t = np.asarray(u.value_in(time_array, u.day), dtype=float)
+        if device:
+            import torch
+            if torch.cuda.is_available():
+                from .engine import DeviceEngine
+                return lightcurve.planet_signal_device(DeviceEngine.get(), t, self.planet_spectrum,
+                                                       self.ldcoeffs, **self._orbit())
         return lightcurve.planet_signal(t, self.planet_spectrum, self.ldcoeffs, **self._orbit())
 
     # -- the visit ------------------------------------------------------------
