@@ -92,7 +92,9 @@ class WFC3_IR(object):
     def get_initial_bias(self):
         """266 x 266 float64 initial bias used as the zero read of SUBARRAY=256
         exposures (exposure_generator.py:456-458)."""
-        return np.load(self.initial_bias)['bias'].astype(np.float64)
+        if getattr(self, '_bias', None) is None:
+            self._bias = np.load(self.initial_bias)['bias'].astype(np.float64)
+        return self._bias.copy()
 
     # ------------------------------------------------------------------
     # mode tables
