@@ -215,6 +215,37 @@ def cpu_reference_exposure(wk, inp, n_sub, threads=None):
                     best, threads = el, t
         else:
             threads = 1
+    # B1: the reference's native kernel alone on one sub-sample's
+    # inputs -- PSF() through ctypes and apply_psf() through the unmodified Cython wrapper
+    psf_alone = None
+    if kind == 'reference':
+        a_, b_ = (E.G141_TRACE, E.G141_WLSOL) if wk['grism'] == 'G141' else (E.G102_TRACE, E.G102_WLSOL)
+        lim = E.WL_LIMITS[wk['grism']]
+        i0, i1 = E.crop_spectrum_ind(lim[0], lim[1], inp['wl'])
+        s_wl = inp['wl'][i0:i1]
+        ratio, sigl, sigh, sens, dwl = E.bin_tables(s_wl, cal['sens_wl_um'], cal['sens_val'])
+        L_ = 1014 if wk['sub'] == 1024 else wk['sub']
+        tr = E.Trace(wk['x_ref'], wk['y_ref'] + 50.0, a_, b_)
+        sub_scale = 507 - wk['sub'] // 2
+        xs, ys = tr.wl_to_x(s_wl) - sub_scale, tr.wl_to_y(s_wl) - sub_scale
+        cnt = np.random.RandomState(3).poisson(
+            E.expected_counts(inp['flux'][i0:i1], None, sens, dwl, float(np.median(dur)), None)).astype(np.int32)
+        sweep = {}
+        for t in [t for t in (1, 2, 4, 8, 16, 32) if t <= ncpu]:
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                OP.psf_reference(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, t)
+                el = time.perf_counter() - t0
+                best = el if best is None or el < best else best
+            sweep[str(t)] = round(cnt.sum() / best / 1e6, 2)
+        psf_alone = {'electrons_per_call': int(cnt.sum()), 'Melectrons_per_s_by_threads': sweep}
+        pyx = OP.reference_pyparallel()
+        if pyx is not None:
+            t0 = time.perf_counter()
+            pyx.apply_psf(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, 1)
+            psf_alone['apply_psf_cython_Melectrons_per_s_1thread'] = round(
+                cnt.sum() / (time.perf_counter() - t0) / 1e6, 2)
     kw = frame_kwargs(wk, 0)
     t0 = time.perf_counter()
     o = E.scanning_frame(cal, wk['grism'], wk['sub'], inp['read_times'], inp['wl'], inp['flux'], depth,
@@ -230,7 +261,8 @@ def cpu_reference_exposure(wk, inp, n_sub, threads=None):
             'sample': '%d of %d sub-samples (evenly spread) + all %d read reductions + post-exposure chain, '
                       'sub-sample time scaled by %d/%d; %.1f s of CPU work' % (
                           len(picks), N, len(ri), N, len(picks), wall),
-            'seconds_per_exposure': per_exposure, 'photons_per_exposure': photons}
+            'seconds_per_exposure': per_exposure, 'photons_per_exposure': photons,
+            'psf_alone': psf_alone}
     return per_exposure, info
 
 
@@ -255,7 +287,8 @@ def run_reference(args, wk):
             'data': 'synthetic', 'photons_per_s': info['photons_per_exposure'] / sec,
             'config': {'workload': wk['desc'], 'rng': 'numpy+rand_r (reference streams)'},
             'cpu_baseline': {'value': val, 'unit': 'exposures/s', 'cores': info['cores'],
-                             'kind': info['kind'], 'sample': info['sample']},
+                             'kind': info['kind'], 'sample': info['sample'],
+                             'native_kernel_alone': info['psf_alone']},
             'e2e': {'value': val, 'unit': 'exposures/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -477,6 +510,8 @@ def run_native(args, wk):
                   'peak_source': 'wb200_microbench(7): Philox4x32-10 + fp32 Box-Muller only, all SMs, this run',
                   'frac': (photons / (t_throw * 1e-3) / 1e9 / rng_peak) if rng_peak else None,
                   'smem_atomic_peaks_gops': {'psf_like_3x3': atom_psf, 'conflict_free': atom_free},
+                  'mufu_bound_gelectron_s': (148 * 16 * (clocks['sm_mhz'] if clocks and clocks.get('sm_mhz')
+                                                        else 1965.0) * 1e6 / 4) / 1e9,
                   'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
     dominant = max(stages.items(), key=lambda kv: kv[1][0])[0]
     line = {
@@ -512,7 +547,10 @@ def run_native(args, wk):
         sec, info = cpu_reference_exposure(wk, inp, 4 * len(inp['read_index']))
         line['cpu_baseline'] = {'value': 1.0 / sec, 'unit': 'exposures/s', 'cores': info['cores'],
                                 'kind': info['kind'], 'sample': info['sample'],
-                                'photons_per_s': info['photons_per_exposure'] / sec}
+                                'photons_per_s': info['photons_per_exposure'] / sec,
+                                'native_kernel_alone': info['psf_alone'],
+                                'note': 'lower bound on the reference time: numpy restatement without astropy '
+                                        'unit algebra, calibration FITS read once instead of per read'}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

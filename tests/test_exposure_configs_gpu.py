@@ -112,3 +112,44 @@ def test_empty_spectrum_and_offframe_trace(calb_dir):
     assert 0 < lit < 0.6 * o['photons']
     for r, want in enumerate(o['reads']):
         assert np.array_equal(exp.reads[r][0], want)
+
+
+def test_output_options_and_missing_dark(calb_dir):
+    """float32 output, device-resident result, and the reference's "no dark file ->
+    warn and switch dark off" behaviour (exposure_generator.py:414-423)."""
+    import warnings
+
+    import torch
+    from wayne import detector, grism
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator, WFC3SimNoDarkFileWarning
+    wl, flux, planet = harness.spectrum(level=2.0e-14)
+    args = (404.5, 457.4, 0.02, 0.02, wl * u.micron, flux, None, 7.4325 * u.pixel / u.s, 500 * u.ms)
+    kw = dict(cosmic_rate=11., sky_background=2.0 * u.count / u.s, rng_key=(5, 6))
+
+    def gen(sub=256, seq='SPARS10', nsamp=5):
+        return ExposureGenerator(detector.WFC3_IR(), grism.G141(), nsamp, seq, sub, None, rng='philox')
+
+    ref = gen().scanning_frame(*args, **kw)
+    f32 = gen().scanning_frame(*args, out_dtype=np.float32, **kw)
+    assert f32.reads[-1][0].dtype == np.float32
+    assert np.array_equal(f32.reads[-1][0], ref.reads[-1][0].astype(np.float32))
+    dev = gen().scanning_frame(*args, device_result=True, **kw)
+    assert isinstance(dev.device_reads, torch.Tensor) and dev.device_reads.is_cuda
+    assert np.array_equal(dev.device_reads.cpu().numpy()[-1], ref.reads[-1][0])
+    assert float(u.value_in(ref.exp_info['sim_time'], u.s)) > 0
+    # SUBARRAY 512 / SPARS25 has no super-dark in the synthetic set written for this session
+    from wayne_b200 import params
+    import os
+    name = detector.WFC3_IR()._dark_file(512, 'SPARS25')
+    path = os.path.join(params._calb_dir, name)
+    if os.path.exists(path):
+        os.remove(path)
+    eg = gen(512, 'SPARS25', 3)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        exp = eg.scanning_frame(650.0, 500.0, 0.02, 0.02, wl * u.micron, flux, None, 1.0 * u.pixel / u.s,
+                                2000 * u.ms, **kw)
+        assert len(exp.reads) == 3
+    assert any(issubclass(x.category, WFC3SimNoDarkFileWarning) for x in w)
+    assert exp.exp_info['add_dark'] is False
