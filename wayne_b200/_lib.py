@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwayne_b200.so")
+LIB_PATH = os.environ.get("WAYNE_B200_LIB") or os.path.join(HERE, "libwayne_b200.so")
 
 OK = 0
 RNG_PHILOX, RNG_RANDR, RNG_HOST = 0, 1, 2

@@ -461,8 +461,11 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
               (unsigned long long)q);
 }
 
+#ifndef WB_THROW_MIN_BLOCKS
+#define WB_THROW_MIN_BLOCKS 5
+#endif
 template <int TW, int TH, bool DIRECT>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, WB_THROW_MIN_BLOCKS)
 k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_args ga)
 {
     const wb200_photon_args &a = p.a;
