@@ -22,7 +22,7 @@ import collections
 
 import numpy as np
 
-from . import lightcurve, sharding, tools
+from . import lightcurve, sharding
 from . import units as u
 from .exposure_generator import ExposureGenerator
 from .trend_generators import visit_trends
