@@ -34,7 +34,7 @@ def _poisson_draws(lam, n_samples=256, n_bins=4096, key=(7, 9)):
     return c.ravel()
 
 
-@pytest.mark.parametrize("lam", [0.05, 0.7, 3.0, 9.99, 10.0, 14.7, 60.0, 243.0, 4000.0, 2.5e5])
+@pytest.mark.parametrize("lam", [0.05, 0.7, 3.0, 9.99, 10.0, 14.7, 39.9, 40.0, 60.0, 243.0, 4000.0, 2.5e5])
 def test_poisson_sampler_distribution(lam):
     x = _poisson_draws(lam)
     n = x.size
