@@ -141,3 +141,15 @@ def test_sky_poisson_and_background_noise():
     assert abs(d3.mean() - (14.7 * 4 + 2.0)) < 5 * np.sqrt((58.8 + 1.0) / n)
     assert abs(d3.var() - (58.8 + 1.0)) < 1.5
     assert np.all(out[:, :5, :] == 0) and np.all(out[:, :, -5:] == 0)   # reference pixels stay 0
+
+
+def test_sky_poisson_has_no_outliers():
+    """30 M sky draws at lam = 14.7: nothing beyond the 1e-9 quantile region
+    (guards the fp32 inversion's u -> 1 and saturated-sum corner cases)."""
+    worst = 0.0
+    for key in range(6):
+        out = _reads_noise_only(sky_rate=14.7, F=1024, R=3, key=(11, key))
+        inner = out[1, 5:-5, 5:-5]                       # first interval: Poisson(14.7)
+        worst = max(worst, float(inner.max()))
+        assert inner.min() >= 0
+    assert worst <= 14.7 + 8.5 * np.sqrt(14.7), worst    # P(X > 47) ~ 1e-11 per draw

@@ -215,18 +215,26 @@ __device__ __forceinline__ float log1p_f(float d)
 // acceptance test (which for lam ~ 16 rejects the squeeze 55% of the time).
 // Probabilities carry ~1e-6 relative error (fp32 running sum), far below what
 // any test of the distribution can resolve.
-__device__ __forceinline__ long long poisson_inversion_f(PhiloxStream &g, float lam)
+__device__ __forceinline__ long long poisson_inversion_u(float u, float lam)
 {
-    const float u = (float)g.uniform();
+    // u is clamped below 1 (a double uniform can round to 1.0f) and the search
+    // stops once the terms no longer move the fp32 sum: the quantile is then
+    // ~lam + 5.5 sigma, i.e. the tail is truncated at the 1 - 6e-8 level
+    u = fminf(u, 0.99999994f);
     float p = expf(-lam), s = p;
     int k = 0;
-    const int kmax = (int)(lam + 12.0f * sqrtf(lam) + 24.0f);
-    while (u > s && k < kmax) {
+    while (u > s) {
         ++k;
         p *= __fdividef(lam, (float)k);
         s += p;
+        if (p < 1e-10f && (float)k > lam)
+            break;
     }
     return k;
+}
+__device__ __forceinline__ long long poisson_inversion_f(PhiloxStream &g, float lam)
+{
+    return poisson_inversion_u((float)g.uniform(), lam);
 }
 
 __device__ inline long long poisson_draw_fast(PhiloxStream &g, double lam)

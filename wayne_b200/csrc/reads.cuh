@@ -162,6 +162,11 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                     load_pair(a.d_draw_noise + (size_t)r * plane, p, dn);
                 if (a.add_sky && a.d_draw_sky)
                     load_pair(a.d_draw_sky + (size_t)r * plane, p, ds);
+                // FAST: one Philox call per (pixel pair, read) feeds both pixels' sky
+                // uniforms (x, y) and the pair's dark normals (z, w)
+                uint4 qs = make_uint4(0, 0, 0, 0);
+                if (FAST && ((a.add_sky && !a.d_draw_sky) || (a.add_dark && !a.d_draw_dark)))
+                    qs = philox4x32_10(make_uint4(1u, (uint32_t)p, (uint32_t)r, WB_STREAM_SKY), a.key0, a.key1);
                 for (int h = 0; h < 2; ++h) {
                     double px = 0.0;
                     if (inside[h]) {
@@ -190,7 +195,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                                 const double lam = a.sky_f32
                                     ? (double)__fmul_rn(__double2float_rn(sky[h]), __double2float_rn(bg))
                                     : sky[h] * bg;
-                                px = px + (double)(FAST ? poisson_draw_fast(g, lam) : poisson_draw(g, lam));
+                                if (FAST && lam < 40.0)
+                                    px = px + (double)poisson_inversion_u((float)u01d(h ? qs.y : qs.x), (float)lam);
+                                else
+                                    px = px + (double)(FAST ? poisson_draw_fast(g, lam) : poisson_draw(g, lam));
                             }
                         }
                         if (chead[h] >= 0) {
@@ -215,13 +223,14 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                         double dk[2], de[2];
                         load_pair(a.d_dark + (size_t)r * plane, p, dk);
                         load_pair(a.d_dark_err + (size_t)r * plane, p, de);
-                        const uint4 q = philox4x32_10(
-                            make_uint4(0, (uint32_t)p, (uint32_t)r, WB_STREAM_DARK), a.key0, a.key1);
                         double z[2];
-                        if (FAST)
-                            box_muller_fd(q.x, q.y, z[0], z[1]);
-                        else
+                        if (FAST) {
+                            box_muller_fd(qs.z, qs.w, z[0], z[1]);
+                        } else {
+                            const uint4 q = philox4x32_10(
+                                make_uint4(0, (uint32_t)p, (uint32_t)r, WB_STREAM_DARK), a.key0, a.key1);
                             box_muller_d(q.x, q.y, z[0], z[1]);
+                        }
                         for (int h = 0; h < 2; ++h) {
                             const double sd = (de[h] > 0) ? de[h] : 0.00001; // detector.py:189-190
                             v[h] = v[h] + (dk[h] + sd * z[h]);
