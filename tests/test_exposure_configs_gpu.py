@@ -153,3 +153,28 @@ def test_output_options_and_missing_dark(calb_dir):
         assert len(exp.reads) == 3
     assert any(issubclass(x.category, WFC3SimNoDarkFileWarning) for x in w)
     assert exp.exp_info['add_dark'] is False
+
+
+def test_direct_path_full_frame_matches_gather_path(calb_dir, monkeypatch):
+    """Native mode at SUBARRAY 1024 / G102 (flat index wrap, offset -5): fused
+    tile-flush accumulation == windows + ordered gather, same Philox electrons."""
+    from wayne import detector, grism
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator
+    from wayne_b200 import calibration, params
+    calibration.write_synthetic_calibration(calb_dir, modes=((1024, 'RAPID'),))
+    wl, flux, planet = harness.spectrum(n_wl=400, lo=0.7, hi=1.25, level=2.0e-14)
+    out = {}
+    for direct in (True, False):
+        monkeypatch.setattr(params, 'direct_accumulation', direct)
+        eg = ExposureGenerator(detector.WFC3_IR(), grism.G102(), 4, 'RAPID', 1024, None, rng='philox')
+        exp = eg.scanning_frame(8.0, 12.0, 0.02, 0.02, wl * u.micron, flux, None, 25.0 * u.pixel / u.s,
+                                400 * u.ms, add_dark=False, cosmic_rate=None,
+                                sky_background=0 * u.count / u.s, add_non_linear=False,
+                                add_read_noise=False, rng_key=(9, 9))
+        out[direct] = (np.array([r[0] for r in exp.reads]), eg.photons)
+    assert out[True][1] == out[False][1] > 1e6
+    a, b = out[True][0], out[False][0]
+    assert b.max() > 10 and np.abs(a - b).max() / b.max() < 1e-7
+    # the source sits in the corner: light reaches the first rows/columns of the light-sensitive area
+    assert b[-1][5:40, 5:200].sum() > 0
