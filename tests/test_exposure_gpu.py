@@ -280,3 +280,38 @@ def test_chebyshev_planet_signal_equals_array_signal(calb_dir):
         outs.append((np.array([r[0] for r in exp.reads]), eg.photons))
     assert outs[0][1] == outs[1][1] > 1e6
     assert np.array_equal(outs[0][0], outs[1][0])
+
+
+def test_config2_explicit_photon_list_bit_exact(calb_dir):
+    """BASELINE configs[1]: G141 staring, 256 subarray, NSAMP=5, the photon list
+    supplied explicitly (counts from the shared numpy stream, normals as the A
+    table of PSF()): int32 histograms and all five reads bit-exact."""
+    from wayne import units as u
+    cal = harness.oracle_calibration()
+    wl, flux, planet = harness.spectrum(level=2.5e-15, n_wl=4096, lo=0.95, hi=1.8)
+    eg = _gen()
+    _, mid, dur, ri = eg._gen_scanning_sample_times(1 * u.year)
+
+    def normals(i, n):
+        return np.random.default_rng(300 + i).standard_normal(2 * n)
+
+    kw = dict(add_dark=False, cosmic_rate=None, add_non_linear=False, add_read_noise=False)
+    np.random.seed(2)
+    exp = eg.scanning_frame(X_REF, Y_REF, 0.0, 0.0, wl * u.micron, flux, None, 0 * u.pixel / u.s, 1 * u.year,
+                            mid, dur, ri, sky_background=0 * u.count / u.s, electron_normals=normals, **kw)
+    o = E.scanning_frame(cal, 'G141', 256, eg.read_times.to(u.s).value, wl, flux, None, X_REF, Y_REF, 0.0, 0.0,
+                         0.0, 365.25 * 86400e3, np.random.RandomState(2), sky_background=0, psf='normals',
+                         normals=normals, **kw)
+    assert eg.photons == o['photons'] > 5e5
+    for r in range(5):
+        assert np.array_equal(exp.reads[r][0], o['reads'][r]), r
+    # every stochastic term on, supplied as host-drawn planes: still equal to the oracle
+    np.random.seed(2)
+    exp = eg.scanning_frame(X_REF, Y_REF, 0.0, 0.0, wl * u.micron, flux, None, 0 * u.pixel / u.s, 1 * u.year,
+                            mid, dur, ri, sky_background=1.2 * u.count / u.s, cosmic_rate=11.,
+                            electron_normals=normals)
+    o = E.scanning_frame(cal, 'G141', 256, eg.read_times.to(u.s).value, wl, flux, None, X_REF, Y_REF, 0.0, 0.0,
+                         0.0, 365.25 * 86400e3, np.random.RandomState(2), sky_background=1.2, cosmic_rate=11.,
+                         psf='normals', normals=normals)
+    for r in range(5):
+        assert np.max(np.abs(exp.reads[r][0] - o['reads'][r])) <= 1e-9 * 4e4, r

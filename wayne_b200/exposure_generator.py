@@ -210,7 +210,7 @@ class ExposureGenerator(object):
                        add_gain_variations=True, add_non_linear=True, clip_values_det_limits=True,
                        add_read_noise=True, add_stellar_noise=True, add_initial_bias=True,
                        progress_bar=None, threads=2, rng_key=None, exact_newton=None,
-                       out_dtype=np.float64, device_result=False):
+                       out_dtype=np.float64, device_result=False, electron_normals=None):
         """Generate a spatially scanned exposure (see the module docstring).
 
         Units of bare numbers: ``wl`` micron, ``stellar_flux`` erg/(angstrom s
@@ -221,7 +221,11 @@ class ExposureGenerator(object):
         (float64 like the reference, or float32), ``device_result`` (leave the
         reads in HBM as ``exposure.device_reads`` [NSAMP][F][F] and skip the
         device->host copy; ``wl`` / ``stellar_flux`` stay host arrays but
-        ``planet_signal`` may be a CUDA tensor already resident in HBM)."""
+        ``planet_signal`` may be a CUDA tensor already resident in HBM),
+        ``electron_normals`` ('numpy' mode only: callable(sample index, n electrons)
+        -> the table A[2n] of PSF() -- x normals then y normals, pyparallel_menu.c:
+        55-62 -- used instead of the rand_r stream: the fully deterministic photon
+        list of BASELINE configs[1])."""
         from . import _lib
         from .engine import DeviceEngine, ExposureRun
 
@@ -402,7 +406,17 @@ class ExposureGenerator(object):
                 dark = None
             if add_read_noise:
                 draws['rn'] = np.random.standard_normal((R + 1, F, F))
-            run.throw(_lib.RNG_RANDR, seeds=s_rand_seeds, threads=threads, add_flat=add_flat)
+            if electron_normals is not None:
+                totals = counts.astype(np.int64).sum(axis=1)
+                tables = [np.asarray(electron_normals(i, int(totals[i])), dtype=np.float64)
+                          for i in range(num_samples)]
+                for i, t in enumerate(tables):
+                    if t.size != 2 * int(totals[i]):
+                        raise ValueError("electron_normals({}, n) must return 2*n values".format(i))
+                run.throw(_lib.RNG_HOST, normals=np.concatenate(tables) if tables else np.zeros(0),
+                          add_flat=add_flat)
+            else:
+                run.throw(_lib.RNG_RANDR, seeds=s_rand_seeds, threads=threads, add_flat=add_flat)
         else:
             run.counts(_lib.COUNT_POISSON if add_stellar_noise else _lib.COUNT_ROUND, key=key)
             if native_cosmics:
