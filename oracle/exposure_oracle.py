@@ -294,14 +294,6 @@ def gen_orbit_start_times_per_exp(time_array, obs_start_index):
     return t0
 
 
-class Draws(object):
-    """(unused placeholder) Source of the numpy-side random numbers, in the reference's order (A.7).
-    Default: a legacy RandomState (the reference uses the global one)."""
-
-    def __init__(self, seed):
-        self.rs = np.random.RandomState(seed)
-
-
 def scanning_frame(cal, grism, subarray, read_times_s, wl_um, stellar_flux, planet_signal,
                    x_ref, y_ref, x_jitter, y_jitter, scan_speed_px_per_ms, sample_rate_ms,
                    rs, ssv=None, noise_mean=False, noise_std=False, add_dark=True, add_flat=True,
