@@ -315,3 +315,27 @@ def test_config2_explicit_photon_list_bit_exact(calb_dir):
                          psf='normals', normals=normals)
     for r in range(5):
         assert np.max(np.abs(exp.reads[r][0] - o['reads'][r])) <= 1e-9 * 4e4, r
+
+
+def test_native_reads_kernel_equals_generic_kernel_full_chain(calb_dir, monkeypatch):
+    """k_reads_native (shared-memory sky CDF window, FMA Newton with an fp32-seeded
+    reciprocal, magic int64 -> double) against the generic k_reads<0, FAST> on one full
+    native exposure with every term on except the sky (its draws are compared kernel to
+    kernel in test_rng_gpu.py: the ramp's read intervals differ by a millisecond, where the
+    throughput kernel re-uses its window plus a remainder draw): the same Philox draws, so
+    the reads agree to the Newton stopping tolerance (both stop when a step is < 1e-3 DN)."""
+    from wayne import units as u
+    wl, flux, planet = harness.spectrum(level=3.0e-14)
+    out = {}
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv('WB200_GENERIC_READS', '1')
+        eg = _gen(rng='philox')
+        exp = eg.scanning_frame(X_REF, Y_REF, 0.02, 0.02, wl * u.micron, flux, None, 7.4325 * u.pixel / u.s,
+                                200 * u.ms, cosmic_rate=500., sky_background=0 * u.count / u.s,
+                                rng_key=(9, 11))
+        out[generic] = np.array([r[0] for r in exp.reads])
+    monkeypatch.delenv('WB200_GENERIC_READS')
+    a, b = out[False], out[True]
+    assert b.max() > 1e3 and np.isfinite(a).all()
+    assert np.abs(a - b).max() < 2e-3, np.abs(a - b).max()

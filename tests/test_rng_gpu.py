@@ -95,7 +95,8 @@ def test_photon_normals_distribution():
     assert abs(cov / (sx * sy)) < 5 / np.sqrt(n)
 
 
-def _reads_noise_only(read_noise=0.0, sky_rate=0.0, noise=(0.0, 0.0), F=266, R=3, key=(3, 4)):
+def _reads_noise_only(read_noise=0.0, sky_rate=0.0, noise=(0.0, 0.0), F=266, R=3, key=(3, 4), fast=0,
+                      dts=(1.0, 2.0, 4.0), sky_level=1.0):
     import torch
     from wayne_b200 import _lib
     dev = torch.device('cuda', 0)
@@ -108,10 +109,11 @@ def _reads_noise_only(read_noise=0.0, sky_rate=0.0, noise=(0.0, 0.0), F=266, R=3
     a.sky_rate, a.sky_f32 = sky_rate, 1
     a.const_gain = 1.0
     a.read_noise = read_noise
+    a.fast_math = fast
     a.key0, a.key1 = key
-    dt = torch.tensor([1.0, 2.0, 4.0][:R], dtype=torch.float64, device=dev)
+    dt = torch.tensor(list(dts)[:R], dtype=torch.float64, device=dev)
     acc = torch.zeros((R, F, F), dtype=torch.float64, device=dev)
-    sky = torch.ones((F, F), dtype=torch.float64, device=dev)
+    sky = torch.full((F, F), float(sky_level), dtype=torch.float64, device=dev)
     out = torch.empty((R + 1, F, F), dtype=torch.float64, device=dev)
     iters = torch.zeros((16,), dtype=torch.int32, device=dev)
     a.d_dt, a.d_acc, a.d_sky, a.d_out = dt.data_ptr(), acc.data_ptr(), sky.data_ptr(), out.data_ptr()
@@ -120,8 +122,9 @@ def _reads_noise_only(read_noise=0.0, sky_rate=0.0, noise=(0.0, 0.0), F=266, R=3
     return out.cpu().numpy()
 
 
-def test_read_noise_normals():
-    out = _reads_noise_only(read_noise=6.0)
+@pytest.mark.parametrize("fast", [0, 1])
+def test_read_noise_normals(fast):
+    out = _reads_noise_only(read_noise=6.0, fast=fast)
     for r in range(4):
         z = out[r] / 6.0
         assert stats.kstest(z.ravel(), 'norm').pvalue > 1e-4
@@ -130,8 +133,9 @@ def test_read_noise_normals():
     assert abs(np.corrcoef(out[0].ravel(), out[1].ravel())[0, 1]) < 0.02
 
 
-def test_sky_poisson_and_background_noise():
-    out = _reads_noise_only(sky_rate=14.7, noise=(0.5, 0.25))
+@pytest.mark.parametrize("fast", [0, 1])
+def test_sky_poisson_and_background_noise(fast):
+    out = _reads_noise_only(sky_rate=14.7, noise=(0.5, 0.25), fast=fast)
     inner = out[:, 5:-5, 5:-5]
     d1 = inner[1]                       # first interval: Poisson(14.7 * 1) + N(0.5, 0.25)
     n = d1.size
@@ -143,13 +147,65 @@ def test_sky_poisson_and_background_noise():
     assert np.all(out[:, :5, :] == 0) and np.all(out[:, :, -5:] == 0)   # reference pixels stay 0
 
 
-def test_sky_poisson_has_no_outliers():
+@pytest.mark.parametrize("fast", [0, 1])
+def test_sky_poisson_has_no_outliers(fast):
     """30 M sky draws at lam = 14.7: nothing beyond the 1e-9 quantile region
     (guards the fp32 inversion's u -> 1 and saturated-sum corner cases)."""
     worst = 0.0
     for key in range(6):
-        out = _reads_noise_only(sky_rate=14.7, F=1024, R=3, key=(11, key))
+        out = _reads_noise_only(sky_rate=14.7, F=1024, R=3, key=(11, key), fast=fast)
         inner = out[1, 5:-5, 5:-5]                       # first interval: Poisson(14.7)
         worst = max(worst, float(inner.max()))
         assert inner.min() >= 0
     assert worst <= 14.7 + 8.5 * np.sqrt(14.7), worst    # P(X > 47) ~ 1e-11 per draw
+
+
+def _chi2_poisson(x, lam):
+    n = x.size
+    lo = int(max(0, np.floor(lam - 6 * np.sqrt(lam) - 2)))
+    hi = int(np.ceil(lam + 6 * np.sqrt(lam) + 3))
+    edges = np.arange(lo, hi + 1)
+    obs = np.histogram(x, bins=np.append(edges, edges[-1] + 1) - 0.5)[0][:-1]
+    cdf = stats.poisson.cdf(edges - 1, lam)
+    exp = np.diff(np.append(cdf, stats.poisson.cdf(edges[-1], lam)))[: len(obs)] * n
+    sel = exp >= 50
+    chi2 = ((obs[sel] - exp[sel]) ** 2 / exp[sel]).sum()
+    dof = sel.sum() - 1
+    return chi2, dof
+
+
+@pytest.mark.parametrize("lam", [0.3, 4.0, 14.7, 23.9, 24.1, 58.8, 131.0])
+def test_native_reads_sky_poisson_pmf(lam):
+    """k_reads_native's shared-memory CDF window (one draw below a mean of 24, the sum of
+    m window draws above): chi-square of 1 M draws per read interval against the exact pmf,
+    for equal, changing and nearly equal interval lengths (the window is rebuilt when the mean
+    drops or grows by more than 0.25, and serves means up to 0.25 larger together with a
+    Poisson draw of the remainder)."""
+    for dts in ((1.0, 1.0, 1.0), (1.0, 0.5, 1.0), (1.0, 1.01, 1.012)):
+        out = _reads_noise_only(sky_rate=lam, F=1034, R=3, key=(5, 6), fast=1, dts=dts, sky_level=1.0)
+        inner = out[:, 5:-5, 5:-5]
+        for r in range(3):
+            x = (inner[r + 1] - inner[r]).ravel()
+            assert np.all(x == np.rint(x)) and x.min() >= 0
+            chi2, dof = _chi2_poisson(x, lam * dts[r])
+            assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (lam, dts, r, chi2, dof)
+        # draws of different read intervals are independent
+        a, b = (inner[1] - inner[0]).ravel(), (inner[2] - inner[1]).ravel()
+        assert abs(np.corrcoef(a, b)[0, 1]) < 5 / np.sqrt(a.size)
+
+
+def test_native_reads_equal_generic_fast_kernel(monkeypatch):
+    """The throughput kernel keeps the Philox counters of k_reads<0, FAST>: same sky draws
+    (window search == serial walk, for every draw) and the same normals."""
+    kw = dict(read_noise=6.0, sky_rate=14.7, noise=(0.5, 0.25), F=522, R=3, key=(21, 22), fast=1,
+              dts=(1.0, 1.0, 1.5))          # means below 24: one window draw == the serial walk
+    new = _reads_noise_only(**kw)
+    monkeypatch.setenv('WB200_GENERIC_READS', '1')
+    old = _reads_noise_only(**kw)
+    monkeypatch.delenv('WB200_GENERIC_READS')
+    assert np.max(np.abs(new - old)) < 1e-4          # ftz / non-ftz SFU forms only
+    sky_only = dict(sky_rate=9.3, F=522, R=3, key=(23, 24), fast=1, dts=(1.0, 2.0, 2.5))
+    new = _reads_noise_only(**sky_only)
+    monkeypatch.setenv('WB200_GENERIC_READS', '1')
+    old = _reads_noise_only(**sky_only)
+    assert np.array_equal(new, old)

@@ -215,17 +215,25 @@ __device__ __forceinline__ float log1p_f(float d)
 // acceptance test (which for lam ~ 16 rejects the squeeze 55% of the time).
 // Probabilities carry ~1e-6 relative error (fp32 running sum), far below what
 // any test of the distribution can resolve.
+__device__ __forceinline__ float rcp_ftz(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ long long poisson_inversion_u(float u, float lam)
 {
     // u is clamped below 1 (a double uniform can round to 1.0f) and the search
     // stops once the terms no longer move the fp32 sum: the quantile is then
-    // ~lam + 5.5 sigma, i.e. the tail is truncated at the 1 - 6e-8 level
+    // ~lam + 5.5 sigma, i.e. the tail is truncated at the 1 - 6e-8 level.
+    // (reads_native.cuh tabulates exactly these partial sums: keep the operations
+    // of the recurrence -- p *= lam * rcp(k); s += p -- identical there.)
     u = fminf(u, 0.99999994f);
     float p = expf(-lam), s = p;
     int k = 0;
     while (u > s) {
         ++k;
-        p *= __fdividef(lam, (float)k);
+        p *= lam * rcp_ftz((float)k);
         s += p;
         if (p < 1e-10f && (float)k > lam)
             break;

@@ -16,6 +16,7 @@
 #include "philox.cuh"
 #include "photons.cuh"
 #include "reads.cuh"
+#include "reads_native.cuh"
 #include "stage1.cuh"
 
 namespace wb {
@@ -351,6 +352,22 @@ int wb200_reads(const wb200_reads_args *a, void *stream)
         WB_LAUNCHED("k_reads<1>");
         k_reads<2><<<blocks, 256, 0, st>>>(*a);
         WB_LAUNCHED("k_reads<2>");
+    } else if (a->fast_math && !a->d_draw_noise && !a->d_draw_sky && !a->d_draw_dark && !a->d_draw_rn &&
+               !getenv("WB200_EXACT_READS") && !getenv("WB200_GENERIC_READS")) {
+        // native mode without host-drawn planes: the throughput kernel (reads_native.cuh)
+        static const size_t smem = RN_SMEM;
+        static const cudaError_t attr64 = cudaFuncSetAttribute(
+            k_reads_native<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static const cudaError_t attr32 = cudaFuncSetAttribute(
+            k_reads_native<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        WB_CUDA(attr64);
+        WB_CUDA(attr32);
+        const int nblocks = (int)((pairs + RN_THREADS - 1) / RN_THREADS);
+        if (a->out_f32)
+            k_reads_native<true><<<nblocks, RN_THREADS, smem, st>>>(*a);
+        else
+            k_reads_native<false><<<nblocks, RN_THREADS, smem, st>>>(*a);
+        WB_LAUNCHED("k_reads_native");
     } else {
         if (a->fast_math && !getenv("WB200_EXACT_READS"))
             k_reads<0, true><<<blocks, 256, 0, st>>>(*a);
