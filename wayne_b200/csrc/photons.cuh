@@ -116,6 +116,76 @@ __device__ __forceinline__ void to_window(const wb200_photon_args &a, int s_loca
         atomicAdd((unsigned long long *)a.d_lost, 1ull);
 }
 
+// Random stream of the native thrower: Philox4x32-10 with a FIXED key, so the ten
+// round keys are instruction immediates (a run-time key costs ~9 constant loads per
+// call: ptxas re-loads kernel parameters inside the loop whatever the register
+// budget), over the counter
+//     (unit j of the bin, hy + sub-sample, bin, hw ^ WB_STREAM_PHOTONS)
+// where (hy, hw) is a 64-bit hash of the exposure's (key0, key1) made on the host
+// (wb::throw_keys).  Philox is a bijection of the counter for any key, so distinct
+// (exposure, sub-sample, bin, unit) give distinct blocks; two exposures could only
+// share blocks if their hashed words collided to within the sample / stream range
+// (probability ~2^-49 per pair of exposures).
+constexpr uint32_t WB_TK0 = 0xA4093822u, WB_TK1 = 0x299F31D0u; // key: hex digits of pi
+constexpr uint32_t WB_PHILOX_M0 = 0xD2511F53u, WB_PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t WB_PHILOX_W0 = 0x9E3779B9u, WB_PHILOX_W1 = 0xBB67AE85u;
+
+struct ThrowKeys {
+    uint32_t hy, hw;
+};
+
+__host__ __device__ inline ThrowKeys throw_keys(uint32_t key0, uint32_t key1)
+{
+    unsigned long long z = ((unsigned long long)key1 << 32 | key0) + 0x9E3779B97F4A7C15ull; // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return ThrowKeys{(uint32_t)z, (uint32_t)(z >> 32)};
+}
+
+// rounds 2..10 of Philox4x32-10 under the fixed key (round 1 is done by the caller,
+// which caches its bin-dependent half)
+// 32 x 32 -> (lo, hi) as two 32-bit registers (one IMAD.WIDE; written in PTX so that
+// NVVM does not widen the xors that follow to 64 bits)
+__device__ __forceinline__ void mul_wide(uint32_t a, uint32_t m, uint32_t &lo, uint32_t &hi)
+{
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(lo), "=r"(hi)
+        : "r"(a), "r"(m));
+}
+template <int R>
+__device__ __forceinline__ uint4 philox_round_fixed(uint4 c)
+{
+    constexpr uint32_t k0 = WB_TK0 + (uint32_t)R * WB_PHILOX_W0, k1 = WB_TK1 + (uint32_t)R * WB_PHILOX_W1;
+    uint32_t lo0, hi0, lo1, hi1;
+    mul_wide(c.x, WB_PHILOX_M0, lo0, hi0);
+    mul_wide(c.z, WB_PHILOX_M1, lo1, hi1);
+    return make_uint4((hi1 ^ c.y) ^ k0, lo1, (hi0 ^ c.w) ^ k1, lo0);
+}
+__device__ __forceinline__ uint4 philox4x32_rounds2to10_fixed(uint4 c)
+{
+    c = philox_round_fixed<1>(c);
+    c = philox_round_fixed<2>(c);
+    c = philox_round_fixed<3>(c);
+    c = philox_round_fixed<4>(c);
+    c = philox_round_fixed<5>(c);
+    c = philox_round_fixed<6>(c);
+    c = philox_round_fixed<7>(c);
+    c = philox_round_fixed<8>(c);
+    c = philox_round_fixed<9>(c);
+    return c;
+}
+
+// the whole call: counter (unit j, hy + sub-sample, bin, hw ^ WB_STREAM_PHOTONS)
+__device__ __forceinline__ uint4 philox4x32_10_throw(uint32_t j, uint32_t sample, uint32_t bin, ThrowKeys k)
+{
+    uint32_t lo0, hi0, lo1, hi1;
+    mul_wide(j, WB_PHILOX_M0, lo0, hi0);
+    mul_wide(bin, WB_PHILOX_M1, lo1, hi1);
+    return philox4x32_rounds2to10_fixed(make_uint4((hi1 ^ (k.hy + sample)) ^ WB_TK0, lo1,
+                                                   (hi0 ^ (k.hw ^ WB_STREAM_PHOTONS)) ^ WB_TK1, lo0));
+}
+
 template <int MODE, int TW, int TH>
 __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
 {
@@ -255,9 +325,8 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
                 if (q >= total)
                     continue;
                 const int j = q - uex;
-                const uint4 r = philox4x32_10(
-                    make_uint4((uint32_t)j, (uint32_t)(wb + b), (uint32_t)s_glob, WB_STREAM_PHOTONS),
-                    a.key0, a.key1);
+                const uint4 r = philox4x32_10_throw((uint32_t)j, (uint32_t)s_glob, (uint32_t)(wb + b),
+                                                    throw_keys(a.key0, a.key1));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int k = 2 * j + h;
@@ -362,20 +431,13 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
 // Same counters as the generic kernel -- (pair index, bin, sample, stream) -- so
 // a given key throws the same electrons whatever the launch geometry.
 // ---------------------------------------------------------------------------
-struct PhiloxKeys {
-    uint32_t k0[10], k1[10];
-};
-
-__device__ __forceinline__ uint4 philox4x32_10_keys(uint4 c, const PhiloxKeys &k)
+// keeps a CTA-uniform value in a vector register instead of letting ptxas rebuild it
+// from the kernel parameters every iteration
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v)
 {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x;
-        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c.z;
-        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.k0[r], (uint32_t)p1,
-                       (uint32_t)(p0 >> 32) ^ c.w ^ k.k1[r], (uint32_t)p0);
-    }
-    return c;
+    uint32_t r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 __device__ __forceinline__ float sqrt_approx(float x)
@@ -417,7 +479,9 @@ __device__ __forceinline__ int floor_magic(float v)
 }
 
 struct BinPar {        // 32 bytes, two 128-bit shared loads
-    int excl, units, cnt, nh;
+    int units;         // Philox calls of the bin: ceil(count / 2), two electrons each
+    int jc;            // units below jc hold two electrons (count >> 1)
+    int jh, jha;       // unit j: electron 2j is wide for j < jha, electron 2j+1 for j < jh
     float fx, fy, sl, sh;
 };
 
@@ -466,10 +530,10 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
 #endif
 template <int TW, int TH, bool DIRECT>
 __global__ void __launch_bounds__(256, WB_THROW_MIN_BLOCKS)
-k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_args ga)
+k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_args ga)
 {
     const wb200_photon_args &a = p.a;
-    extern __shared__ int tile[]; // TH*TW
+    extern __shared__ int tile[]; // TH*TW, then one spare word (electrons outside the accepted range)
     __shared__ float s_red[4][8];
     __shared__ int s_org[2];
     __shared__ __align__(16) BinPar s_bin[8][32];
@@ -573,24 +637,26 @@ k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_a
     // of accepted (ix, iy) is tile_acc + (iy*TW + ix)*4 in the shared window
     const int ax0 = tx0 + lox, ay0 = ty0 + loy;
     const uint32_t tile_acc = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)((loy * TW + lox) * 4);
+    const uint32_t dump = pin_reg((uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(TW * TH * 4));
+    // round-1 constants of the thrower's Philox stream (see ThrowKeys)
+    const uint32_t cyk = (keys.hy + s_glob) ^ WB_TK0;
+    const uint32_t cwk = pin_reg((keys.hw ^ WB_STREAM_PHOTONS) ^ WB_TK1);
 
     const int ngroups = (w1 - w0 + 31) >> 5;
     for (int g = warp; g < ngroups; g += nwarps) {
         const int wb = w0 + (g << 5);
         const int w = wb + lane;
         BinPar bp;
-        bp.cnt = 0;
-        bp.nh = 0;
+        int cnt = 0, nh = 0;
         bp.fx = bp.fy = bp.sl = bp.sh = 0.f;
         if (w < w1) {
-            const int cnt = a.d_counts[row + w];
+            cnt = a.d_counts[row + w];
             if (cnt > 0) {
                 double bx, by;
                 bin_xy(w, bx, by);
-                bp.cnt = cnt;
                 // first N = (int)(counts*ratio) electrons take the wide Gaussian
                 // (pyparallel_menu.c:89-98)
-                bp.nh = __double2int_rz((double)cnt * a.d_ratio[w]);
+                nh = __double2int_rz((double)cnt * a.d_ratio[w]);
                 bp.fx = (float)(bx - (double)ax0);
                 bp.fy = (float)(by - (double)ay0);
                 bp.sl = (float)a.d_sigl[w];
@@ -599,18 +665,23 @@ k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_a
                 // positions, NaN widths (the reference's INT_MIN path), and widths
                 // beyond 1e5 px (keeps |coordinate| < 2^22 for floor_magic)
                 bool bad = !(fabsf(bp.fx) < 3.0e6f) || !(fabsf(bp.fy) < 3.0e6f);
-                if (bp.nh > 0 && !(fabsf(bp.sh) <= 1.0e5f))
+                if (nh > 0 && !(fabsf(bp.sh) <= 1.0e5f))
                     bad = true;
-                if (bp.cnt - bp.nh > 0 && !(fabsf(bp.sl) <= 1.0e5f))
+                if (cnt - nh > 0 && !(fabsf(bp.sl) <= 1.0e5f))
                     bad = true;
                 if (bad)
-                    bp.cnt = 0;
+                    cnt = 0;
+            } else {
+                cnt = 0;
             }
         }
-        bp.units = (bp.cnt + 1) >> 1;
+        nh = max(0, min(nh, cnt));
+        bp.units = (cnt + 1) >> 1;
+        bp.jc = cnt >> 1;
+        bp.jh = nh >> 1;
+        bp.jha = (nh + 1) >> 1;
         const int incl = warp_incl_scan(bp.units);
         const int total = __shfl_sync(FULL, incl, 31);
-        bp.excl = incl - bp.units;
         __syncwarp();
         mybins[lane] = bp;
         __syncwarp();
@@ -628,45 +699,52 @@ k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_a
             if (v <= q)
                 b += step;
         }
+        const int excl_b = __shfl_sync(FULL, incl - bp.units, b);
         if (q >= qend)
             continue; // (no collectives below)
         // flat walk over the run (all lanes execute the same body every trip; a
         // lane steps to its next bin when the current one has no units left)
         BinPar cur = mybins[b];
-        int j = q - cur.excl;          // unit index inside the current bin
-        int rem = cur.units - j;       // units of the current bin still to do
-        uint32_t cbin = (uint32_t)(wb + b);
-        for (int n = qend - q; n > 0; --n, ++j, --rem) {
-            while (rem <= 0) {         // next bin with units (empty bins have units == 0)
-                ++b;
-                ++cbin;
-                cur = mybins[b];
+        int j = q - excl_b;            // unit index inside the current bin (< cur.units here)
+        int n = qend - q;              // units of this lane's run still to do
+        // the bin's half of Philox round 1: (hi(M1*bin) ^ c.y ^ k0, lo(M1*bin))
+        uint32_t r1x, r1y;
+        mul_wide((uint32_t)(wb + b), WB_PHILOX_M1, r1y, r1x);
+        r1x ^= cyk;
+        do {
+            if (j >= cur.units) {      // rare: step to the next bin that has units
+                do {
+                    ++b;
+                    cur = mybins[b];
+                } while (cur.units == 0);
                 j = 0;
-                rem = cur.units;
+                mul_wide((uint32_t)(wb + b), WB_PHILOX_M1, r1y, r1x);
+                r1x ^= cyk;
             }
-            const uint4 r = philox4x32_10_keys(make_uint4((uint32_t)j, cbin, s_glob, WB_STREAM_PHOTONS), keys);
+            uint32_t pjl, pjh;
+            mul_wide((uint32_t)j, WB_PHILOX_M0, pjl, pjh);
+            const uint4 r = philox4x32_rounds2to10_fixed(make_uint4(r1x, r1y, pjh ^ cwk, pjl));
             // both electrons of the unit in straight-line code (their MUFU chains
             // interleave); the second is masked off for an odd count's last unit
-            const int k0 = 2 * j;
-            const bool two = (k0 + 1) < cur.cnt;
+            const bool two = j < cur.jc;
             const float u1a = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
             const float u1b = fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
             const float tha = fmaf((float)r.y, 1.4629180792671596e-09f, -3.14159265358979f);
             const float thb = fmaf((float)r.w, 1.4629180792671596e-09f, -3.14159265358979f);
             const float rsa = sqrt_approx(-1.3862943611198906f * lg2_approx(u1a)) *
-                              ((k0 < cur.nh) ? cur.sh : cur.sl);
+                              ((j < cur.jha) ? cur.sh : cur.sl);
             const float rsb = sqrt_approx(-1.3862943611198906f * lg2_approx(u1b)) *
-                              ((k0 + 1 < cur.nh) ? cur.sh : cur.sl);
+                              ((j < cur.jh) ? cur.sh : cur.sl);
             const int ixa = floor_magic(fmaf(cos_approx(tha), rsa, cur.fx));
             const int iya = floor_magic(fmaf(sin_approx(tha), rsa, cur.fy));
             const int ixb = floor_magic(fmaf(cos_approx(thb), rsb, cur.fx));
             const int iyb = floor_magic(fmaf(sin_approx(thb), rsb, cur.fy));
             const bool ina = (unsigned)ixa < nx && (unsigned)iya < ny;
             const bool inb = (unsigned)ixb < nx && (unsigned)iyb < ny;
-            if (ina)
-                red_shared_inc(tile_acc + (uint32_t)(iya * (TW * 4) + ixa * 4));
-            if (inb && two)
-                red_shared_inc(tile_acc + (uint32_t)(iyb * (TW * 4) + ixb * 4));
+            // branch-free increments: an electron outside the accepted range adds to a
+            // spare shared word instead (never read), so the common case has no branch
+            red_shared_inc(ina ? tile_acc + (uint32_t)(iya * (TW * 4) + ixa * 4) : dump);
+            red_shared_inc((inb && two) ? tile_acc + (uint32_t)(iyb * (TW * 4) + ixb * 4) : dump);
             if (!ina || (two && !inb)) { // rare: electrons that left the tile
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -681,7 +759,8 @@ k_throw_philox(const PhotonParams p, const PhiloxKeys keys, const wb200_gather_a
                     }
                 }
             }
-        }
+            ++j;
+        } while (--n > 0);
     }
     __syncthreads();
 

@@ -169,8 +169,16 @@ __global__ void k_trace_positions(int N, int W, const double *__restrict__ trace
     ypos[(size_t)s * W + w] = y;
 }
 
-// exposure_generator.py:344-348 and :602-628.  grid = (ceil(W/256), N).
-__global__ void __launch_bounds__(256)
+// exposure_generator.py:344-348 and :602-628.  grid = (ceil(W/128), ceil(N/COUNTS_SPT)).
+// A thread owns one bin for COUNTS_SPT consecutive sub-samples: the bin's flux,
+// sensitivity and width are loaded once, the next sub-sample's planet-signal load
+// is in flight during the current draw, and the per-sub-sample photon totals leave
+// through one warp reduction + atomic each (no CTA barrier: a warp that is held up in
+// the Poisson rejection loop does not stall the others).
+constexpr int COUNTS_SPT = 4;
+constexpr int COUNTS_THREADS = 128;
+
+__global__ void __launch_bounds__(COUNTS_THREADS, 8)
 k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict__ depth,
          long long depth_ld, const double *__restrict__ cheb_coef, int cheb_order,
          const double *__restrict__ cheb_x, const double *__restrict__ sens,
@@ -178,64 +186,76 @@ k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict
          uint32_t k0, uint32_t k1, double *expected, int *counts, unsigned long long *totals)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
-    long long c = 0;
-    if (w < W) {
-        double f = flux[w];
-        if (cheb_coef) {
-            // Clenshaw recurrence in numpy.polynomial.chebyshev.chebval's order
-            const double *cf = cheb_coef + (size_t)s * cheb_order;
-            const double x = cheb_x[w];
-            double d;
-            if (cheb_order == 1) {
-                d = cf[0];
-            } else {
-                const double x2 = 2 * x;
-                double c0 = cf[cheb_order - 2], c1 = cf[cheb_order - 1];
-                for (int i = 3; i <= cheb_order; ++i) {
-                    const double tmp = c0;
-                    c0 = cf[cheb_order - i] - c1;
-                    c1 = tmp + c1 * x2;
-                }
-                d = c0 + c1 * x;
-            }
-            f = f * (1. - d);
-        } else if (depth)
-            f = f * (1. - depth[(size_t)s * depth_ld + w]);
-        double e = f * sens[w];  // ph / s / angstrom
-        e = e * dwl[w];          // (ph/s/A) * micron
-        e = e * 1e4;             // micron -> angstrom : ph / s
-        e = e * dur_ms[s];       // ph/s * ms
-        e = e * 1e-3;            // ms -> s : photons
-        e = e * scale;           // visit trend (exposure_generator.py:620-621)
-        if (expected)
-            expected[(size_t)s * W + w] = e;
-        if (mode == WB200_COUNT_ROUND) {
-            c = (long long)rint(e);
-        } else if (mode == WB200_COUNT_POISSON) {
-            PhiloxStream g(k0, k1, (uint32_t)w, (uint32_t)s, WB_STREAM_COUNTS);
-            c = poisson_draw_fast(g, e);
-        } else if (counts) {
-            c = counts[(size_t)s * W + w];
-        }
-        if (c < 0)
-            c = 0;
-        if (c > 2147483647LL)
-            c = 2147483647LL; // the reference's counters are 32-bit (pyparallel_menu.c:12)
-        if (mode != WB200_COUNT_NONE && counts)
-            counts[(size_t)s * W + w] = (int)c;
+    const int s0 = blockIdx.y * COUNTS_SPT;
+    const bool live = w < W;
+    double f0 = 0.0, sn = 0.0, dw = 0.0, x = 0.0;
+    const bool use_depth = live && !cheb_coef && depth;
+    double dnext = 0.0;
+    if (live) {
+        f0 = flux[w];
+        sn = sens[w];
+        dw = dwl[w];
+        if (cheb_coef)
+            x = cheb_x[w];
+        if (use_depth && s0 < N)
+            dnext = depth[(size_t)s0 * depth_ld + w];
     }
-    unsigned long long v = warp_sum_u64((unsigned long long)c);
-    __shared__ unsigned long long part[8];
-    if (lane_id() == 0)
-        part[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i)
-            t += part[i];
-        if (t)
-            atomicAdd(&totals[s], t);
+#pragma unroll 1
+    for (int i = 0; i < COUNTS_SPT; ++i) {
+        const int s = s0 + i;
+        if (s >= N)
+            break; // CTA-uniform
+        long long c = 0;
+        const double dcur = dnext;
+        if (use_depth && i + 1 < COUNTS_SPT && s + 1 < N) // next sub-sample's planet signal in flight
+            dnext = depth[(size_t)(s + 1) * depth_ld + w];
+        if (live) {
+            double f = f0;
+            if (cheb_coef) {
+                // Clenshaw recurrence in numpy.polynomial.chebyshev.chebval's order
+                const double *cf = cheb_coef + (size_t)s * cheb_order;
+                double d;
+                if (cheb_order == 1) {
+                    d = cf[0];
+                } else {
+                    const double x2 = 2 * x;
+                    double c0 = cf[cheb_order - 2], c1 = cf[cheb_order - 1];
+                    for (int j = 3; j <= cheb_order; ++j) {
+                        const double tmp = c0;
+                        c0 = cf[cheb_order - j] - c1;
+                        c1 = tmp + c1 * x2;
+                    }
+                    d = c0 + c1 * x;
+                }
+                f = f * (1. - d);
+            } else if (depth)
+                f = f * (1. - dcur);
+            double e = f * sn;       // ph / s / angstrom
+            e = e * dw;              // (ph/s/A) * micron
+            e = e * 1e4;             // micron -> angstrom : ph / s
+            e = e * dur_ms[s];       // ph/s * ms
+            e = e * 1e-3;            // ms -> s : photons
+            e = e * scale;           // visit trend (exposure_generator.py:620-621)
+            if (expected)
+                expected[(size_t)s * W + w] = e;
+            if (mode == WB200_COUNT_ROUND) {
+                c = (long long)rint(e);
+            } else if (mode == WB200_COUNT_POISSON) {
+                PhiloxStream g(k0, k1, (uint32_t)w, (uint32_t)s, WB_STREAM_COUNTS);
+                c = poisson_draw_fast(g, e);
+            } else if (counts) {
+                c = counts[(size_t)s * W + w];
+            }
+            if (c < 0)
+                c = 0;
+            if (c > 2147483647LL)
+                c = 2147483647LL; // the reference's counters are 32-bit (pyparallel_menu.c:12)
+            if (mode != WB200_COUNT_NONE && counts)
+                counts[(size_t)s * W + w] = (int)c;
+        }
+        const unsigned long long v = warp_sum_u64((unsigned long long)c);
+        if (lane_id() == 0 && v)
+            atomicAdd(&totals[s], v);
     }
 }
 

@@ -82,17 +82,10 @@ static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t s
     case WB200_RNG_PHILOX: {
         if (getenv("WB200_GENERIC_THROW") && !direct)      // A/B switch: the baseline generic kernel
             return launch_throw<WB200_RNG_PHILOX>(p, st);
-        PhiloxKeys keys;
-        uint32_t k0 = a->key0, k1 = a->key1;
-        for (int r = 0; r < 10; ++r) {
-            keys.k0[r] = k0;
-            keys.k1[r] = k1;
-            k0 += 0x9E3779B9u;
-            k1 += 0xBB67AE85u;
-        }
+        const ThrowKeys keys = throw_keys(a->key0, a->key1);
         const int chunks = (a->n_bins + a->chunk_bins - 1) / a->chunk_bins;
         dim3 grid(chunks, a->n_samples);
-        const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int);
+        const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int) + 16; // + the spare word
         if (direct) {
             k_throw_philox<TILE_W, TILE_H, true><<<grid, 256, smem, st>>>(p, keys, *direct);
         } else {
@@ -208,8 +201,8 @@ int wb200_counts_ex(const wb200_counts_args *a, void *stream)
                "Chebyshev planet signal: need x and 1 <= order <= 32");
     cudaStream_t st = (cudaStream_t)stream;
     WB_CUDA(cudaMemsetAsync(a->d_totals, 0, sizeof(uint64_t) * a->n_samples, st));
-    dim3 grid((a->n_bins + 255) / 256, a->n_samples);
-    k_counts<<<grid, 256, 0, st>>>(a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld,
+    dim3 grid((a->n_bins + COUNTS_THREADS - 1) / COUNTS_THREADS, (a->n_samples + COUNTS_SPT - 1) / COUNTS_SPT);
+    k_counts<<<grid, COUNTS_THREADS, 0, st>>>(a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld,
                                    a->d_cheb_coef, a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl,
                                    a->d_dur_ms, a->scale, a->count_mode, a->key0, a->key1, a->d_expected,
                                    a->d_counts, (unsigned long long *)a->d_totals);
