@@ -177,8 +177,11 @@ __global__ void k_trace_positions(int N, int W, const double *__restrict__ trace
 // the Poisson rejection loop does not stall the others).
 constexpr int COUNTS_SPT = 4;
 constexpr int COUNTS_THREADS = 128;
+#ifndef COUNTS_MIN_BLOCKS
+#define COUNTS_MIN_BLOCKS 8
+#endif
 
-__global__ void __launch_bounds__(COUNTS_THREADS, 8)
+__global__ void __launch_bounds__(COUNTS_THREADS, COUNTS_MIN_BLOCKS)
 k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict__ depth,
          long long depth_ld, const double *__restrict__ cheb_coef, int cheb_order,
          const double *__restrict__ cheb_x, const double *__restrict__ sens,
