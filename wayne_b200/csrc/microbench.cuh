@@ -53,6 +53,55 @@ __global__ void __launch_bounds__(256) k_mb_global_red(int which, int iters, int
     }
 }
 
+// Issue-rate probes for single instruction kinds (which = 8..12): 64 dependent-free
+// instructions per iteration per thread, 8 independent chains
+template <int which>
+__global__ void __launch_bounds__(256) k_mb_pipe(int iters, int *sink)
+{
+    uint32_t x[8];
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+        f[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (which == 8) {        // IMAD.WIDE.U32: hi ^ lo feeds the next
+                    uint32_t lo, hi;
+                    asm volatile("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+                                 : "=r"(lo), "=r"(hi) : "r"(x[i]), "r"(0xD2511F53u));
+                    x[i] = hi + lo;
+                } else if (which == 9) { // IMAD (32-bit)
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(0xD2511F53u), "r"(0x9E3779B9u));
+                } else if (which == 10) { // LOP3
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[(i + 1) & 7]), "r"(0x9E3779B9u));
+                } else if (which == 11) { // MUFU.LG2
+                    asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+                } else if (which == 12) { // FFMA (3-register form)
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(f[(i + 1) & 7]), "f"(f[(i + 2) & 7]));
+                } else {                 // 13: I2FP.F32.U32 + back (F2I excluded: xor with bits)
+                    float t;
+                    asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(t) : "r"(x[i]));
+                    x[i] ^= __float_as_uint(t);
+                }
+            }
+        }
+    }
+    uint32_t acc = 0;
+    float accf = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc ^= x[i];
+        accf += f[i];
+    }
+    if (acc == 0x7fffffffu || accf == 1.2345f)
+        sink[0] = 1;
+}
+
 // Philox + fp32 Box-Muller pair, no memory: the ALU/SFU ceiling per electron
 __global__ void __launch_bounds__(256) k_mb_rng(int which, int iters, int *sink)
 {

@@ -497,7 +497,7 @@ int *PSF(int *counts, int size, double *x_pos, double *y_pos, double *psf_ratio,
 
 int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
 {
-    WB_REQUIRE(which >= 0 && which <= 7 && iters > 0 && ms_out && ops_out, "bad args");
+    WB_REQUIRE(which >= 0 && which <= 13 && iters > 0 && ms_out && ops_out, "bad args");
     cudaDeviceProp prop;
     int dev = 0;
     WB_CUDA(cudaGetDevice(&dev));
@@ -517,8 +517,20 @@ int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
             k_mb_smem_atomic<<<blocks, 256>>>(which, iters, buf);
         else if (which <= 5)
             k_mb_global_red<<<blocks, 256>>>(which, iters, buf, n);
-        else
+        else if (which <= 7)
             k_mb_rng<<<blocks, 256>>>(which, iters, buf);
+        else if (which == 8)
+            k_mb_pipe<8><<<blocks, 256>>>(iters, buf);
+        else if (which == 9)
+            k_mb_pipe<9><<<blocks, 256>>>(iters, buf);
+        else if (which == 10)
+            k_mb_pipe<10><<<blocks, 256>>>(iters, buf);
+        else if (which == 11)
+            k_mb_pipe<11><<<blocks, 256>>>(iters, buf);
+        else if (which == 12)
+            k_mb_pipe<12><<<blocks, 256>>>(iters, buf);
+        else
+            k_mb_pipe<13><<<blocks, 256>>>(iters, buf);
         WB_LAUNCHED("microbench");
         WB_CUDA(cudaEventRecord(e1));
         WB_CUDA(cudaEventSynchronize(e1));
@@ -534,6 +546,8 @@ int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
     double ops = (double)blocks * 256.0 * iters;
     if (which == 7)
         ops *= 2.0; // two electrons (normal pairs) per Philox call
+    if (which >= 8)
+        ops *= 64.0; // probed instructions per iteration and thread
     *ops_out = ops;
     return WB200_OK;
 }
