@@ -176,14 +176,107 @@ __device__ __forceinline__ uint4 philox4x32_rounds2to10_fixed(uint4 c)
     return c;
 }
 
-// the whole call: counter (unit j, hy + sub-sample, bin, hw ^ WB_STREAM_PHOTONS)
-__device__ __forceinline__ uint4 philox4x32_10_throw(uint32_t j, uint32_t sample, uint32_t bin, ThrowKeys k)
+// the whole call: counter (unit j, hy + sub-sample, bin, hw ^ stream)
+__device__ __forceinline__ uint4 philox4x32_10_throw(uint32_t j, uint32_t sample, uint32_t bin, ThrowKeys k,
+                                                     uint32_t stream = WB_STREAM_PHOTONS)
 {
     uint32_t lo0, hi0, lo1, hi1;
     mul_wide(j, WB_PHILOX_M0, lo0, hi0);
     mul_wide(bin, WB_PHILOX_M1, lo1, hi1);
     return philox4x32_rounds2to10_fixed(make_uint4((hi1 ^ (k.hy + sample)) ^ WB_TK0, lo1,
-                                                   (hi0 ^ (k.hw ^ WB_STREAM_PHOTONS)) ^ WB_TK1, lo0));
+                                                   (hi0 ^ (k.hw ^ stream)) ^ WB_TK1, lo0));
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// u1 >= 2^-33 is never denormal, so the flush-to-zero forms are exact here and
+// save the denormal pre-scaling the non-ftz forms expand to
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sin_approx(float x)
+{
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float cos_approx(float x)
+{
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void red_shared_inc(uint32_t addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+// floor(v) for |v| < 2^22 without a conversion instruction: adding 1.5*2^23
+// with round-toward-minus-infinity leaves floor(v) in the low mantissa bits.
+__device__ __forceinline__ int floor_magic(float v)
+{
+    return __float_as_int(__fadd_rd(v, 12582912.0f)) - 0x4B400000;
+}
+
+// ---- one Philox call = FOUR electrons --------------------------------------------
+// IMAD.WIDE.U32 issues once per 4 cycles per SM sub-partition on B200 (measured:
+// wb200_microbench(8), profiles/), so a Philox4x32-10 call costs ~80 cycles per warp
+// whatever else is in flight: at two electrons per call the multiplier pipe, not
+// the SFU or the shared-memory atomics, bounds the thrower.  Each 32-bit word
+// therefore feeds one electron's Box-Muller pair:
+//     high 16 bits -> radius uniform  u1 = (k + 1/2) 2^-16
+//     low  16 bits -> angle           theta = (t - 32768 + 1/2) 2 pi 2^-16
+// Radius fields k < 16 (2.4e-4 of the electrons: everything beyond 4.08 sigma) are
+// refined with a 32-bit uniform v from a second call (stream WB_STREAM_PHOTON_TAIL,
+// same counter): u1 = (k + v) 2^-16, so the tail is continuous out to 8.2 sigma as
+// with a 49-bit uniform.  In the bulk the radius lattice is finer than 3e-3 sigma
+// (2.6e-5 sigma at the median) and the angle lattice 9.6e-5 rad -- far below a pixel
+// for any PSF width, and tests/test_rng_gpu.py checks the binned distributions
+// against the exact double-Gaussian cell probabilities.
+constexpr uint32_t WB_STREAM_PHOTON_TAIL = 7;
+constexpr uint32_t WB_TAIL_WORD = 16u << 16; // words below this have radius field < 16
+constexpr float WB_ZMAX_THROW = 8.3f;        // sqrt(2 * 49 ln 2) = 8.24
+
+// (float)(2^23 + 16-bit field): one PRMT, no conversion instruction
+__device__ __forceinline__ float hi16_biased(uint32_t w)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632));
+}
+__device__ __forceinline__ float lo16_biased(uint32_t w)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610));
+}
+__device__ __forceinline__ float throw_u1(uint32_t w) // (k + 1/2) 2^-16, exact
+{
+    return fmaf(hi16_biased(w), 1.52587890625e-05f, -127.99999237060547f);
+}
+__device__ __forceinline__ float throw_u1_tail(uint32_t w, uint32_t t) // (k + v) 2^-16
+{
+    const float v = fmaf((float)t, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    return ((hi16_biased(w) - 8388608.0f) + v) * 1.52587890625e-05f;
+}
+__device__ __forceinline__ float throw_theta(uint32_t w) // in (-pi, pi)
+{
+    return fmaf(lo16_biased(w) - 8421376.0f, 9.587379924285257e-05f, 4.793689962142629e-05f);
+}
+// offsets of one electron in units of its PSF sigma (radius * cos, radius * sin)
+__device__ __forceinline__ void throw_offsets(float u1, uint32_t w, float sigma, float &dx, float &dy)
+{
+    const float rs = sqrt_approx(-1.3862943611198906f * lg2_approx(u1)) * sigma; // sqrt(-2 ln u1) sigma
+    const float th = throw_theta(w);
+    dx = cos_approx(th) * rs;
+    dy = sin_approx(th) * rs;
+}
+__device__ __forceinline__ uint32_t word_of(const uint4 &r, int i)
+{
+    return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
 }
 
 template <int MODE, int TW, int TH>
@@ -296,7 +389,10 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
                 cnt = 0;
             }
         }
-        const int units = (MODE == WB200_RNG_PHILOX) ? ((cnt + 1) >> 1) : cnt;
+        // PHILOX: a unit is one Philox call = up to four electrons of one width: the
+        // ceil(nh/4) wide units of the bin come first, then the narrow ones
+        const int nhc = max(0, min(nh, cnt)), uh = (nhc + 3) >> 2;
+        const int units = (MODE == WB200_RNG_PHILOX) ? (uh + ((cnt - nhc + 3) >> 2)) : cnt;
         const int incl = warp_incl_scan(units);
         const int total = __shfl_sync(FULL, incl, 31);
         const int excl = incl - units;
@@ -316,7 +412,8 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
                         b += step;
                 }
                 const int ucnt = __shfl_sync(FULL, cnt, b);
-                const int unh = __shfl_sync(FULL, nh, b);
+                const int unh = __shfl_sync(FULL, nhc, b);
+                const int uuh = __shfl_sync(FULL, uh, b);
                 const int uex = __shfl_sync(FULL, excl, b);
                 const float ux = __shfl_sync(FULL, fx, b);
                 const float uy = __shfl_sync(FULL, fy, b);
@@ -325,21 +422,28 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
                 if (q >= total)
                     continue;
                 const int j = q - uex;
-                const uint4 r = philox4x32_10_throw((uint32_t)j, (uint32_t)s_glob, (uint32_t)(wb + b),
-                                                    throw_keys(a.key0, a.key1));
+                const ThrowKeys tk = throw_keys(a.key0, a.key1);
+                const uint4 r = philox4x32_10_throw((uint32_t)j, (uint32_t)s_glob, (uint32_t)(wb + b), tk);
+                const bool wide = j < uuh;
+                const float sg = wide ? ush : usl;
+                const int rem = wide ? (unh - 4 * j) : (ucnt - unh - 4 * (j - uuh)); // electrons left
+                uint4 t = make_uint4(0, 0, 0, 0);
+                if (min(min(r.x, r.y), min(r.z, r.w)) < WB_TAIL_WORD)
+                    t = philox4x32_10_throw((uint32_t)j, (uint32_t)s_glob, (uint32_t)(wb + b), tk,
+                                            WB_STREAM_PHOTON_TAIL);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = 2 * j + h;
-                    if (k >= ucnt)
+                for (int h = 0; h < 4; ++h) {
+                    if (h >= rem)
                         break;
-                    float zx, zy;
-                    box_muller_f(h ? r.z : r.x, h ? r.w : r.y, zx, zy);
-                    const float sg = (k < unh) ? ush : usl;
+                    const uint32_t wd = word_of(r, h);
+                    const float u1 = (wd < WB_TAIL_WORD) ? throw_u1_tail(wd, word_of(t, h)) : throw_u1(wd);
+                    float dx, dy;
+                    throw_offsets(u1, wd, sg, dx, dy);
                     // floor on tile-relative coordinates == the reference's (int)
                     // truncation on frame coordinates for every accepted electron
                     // (x in (-1,1) is rejected either way by the strict 0 < x test)
-                    const int ix = __float2int_rd(fmaf(zx, sg, ux));
-                    const int iy = __float2int_rd(fmaf(zy, sg, uy));
+                    const int ix = __float2int_rd(dx + ux);
+                    const int iy = __float2int_rd(dy + uy);
                     if (ix >= T.lox && ix < T.hix && iy >= T.loy && iy < T.hiy) {
                         atomicAdd(&tile[iy * TW + ix], 1);
                     } else {
@@ -440,48 +544,11 @@ __device__ __forceinline__ uint32_t pin_reg(uint32_t v)
     return r;
 }
 
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// u1 >= 2^-33 is never denormal, so the flush-to-zero forms are exact here and
-// save the denormal pre-scaling the non-ftz forms expand to
-__device__ __forceinline__ float lg2_approx(float x)
-{
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float sin_approx(float x)
-{
-    float r;
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float cos_approx(float x)
-{
-    float r;
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void red_shared_inc(uint32_t addr)
-{
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-}
-
-// floor(v) for |v| < 2^22 without a conversion instruction: adding 1.5*2^23
-// with round-toward-minus-infinity leaves floor(v) in the low mantissa bits.
-__device__ __forceinline__ int floor_magic(float v)
-{
-    return __float_as_int(__fadd_rd(v, 12582912.0f)) - 0x4B400000;
-}
-
 struct BinPar {        // 32 bytes, two 128-bit shared loads
-    int units;         // Philox calls of the bin: ceil(count / 2), two electrons each
-    int jc;            // units below jc hold two electrons (count >> 1)
-    int jh, jha;       // unit j: electron 2j is wide for j < jha, electron 2j+1 for j < jh
+    int units;         // Philox calls of the bin: ceil(nh/4) wide ones, then ceil(nl/4) narrow ones
+    int uh;            // units below uh are wide
+    int nh;            // wide electrons: unit j < uh holds min(4, nh - 4j)
+    int nlx;           // nl + 4*uh: unit j >= uh holds min(4, nlx - 4j)
     float fx, fy, sl, sh;
 };
 
@@ -676,10 +743,10 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             }
         }
         nh = max(0, min(nh, cnt));
-        bp.units = (cnt + 1) >> 1;
-        bp.jc = cnt >> 1;
-        bp.jh = nh >> 1;
-        bp.jha = (nh + 1) >> 1;
+        bp.uh = (nh + 3) >> 2;
+        bp.units = bp.uh + ((cnt - nh + 3) >> 2);
+        bp.nh = nh;
+        bp.nlx = cnt - nh + 4 * bp.uh;
         const int incl = warp_incl_scan(bp.units);
         const int total = __shfl_sync(FULL, incl, 31);
         __syncwarp();
@@ -724,38 +791,51 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             uint32_t pjl, pjh;
             mul_wide((uint32_t)j, WB_PHILOX_M0, pjl, pjh);
             const uint4 r = philox4x32_rounds2to10_fixed(make_uint4(r1x, r1y, pjh ^ cwk, pjl));
-            // both electrons of the unit in straight-line code (their MUFU chains
-            // interleave); the second is masked off for an odd count's last unit
-            const bool two = j < cur.jc;
-            const float u1a = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-            const float u1b = fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-            const float tha = fmaf((float)r.y, 1.4629180792671596e-09f, -3.14159265358979f);
-            const float thb = fmaf((float)r.w, 1.4629180792671596e-09f, -3.14159265358979f);
-            const float rsa = sqrt_approx(-1.3862943611198906f * lg2_approx(u1a)) *
-                              ((j < cur.jha) ? cur.sh : cur.sl);
-            const float rsb = sqrt_approx(-1.3862943611198906f * lg2_approx(u1b)) *
-                              ((j < cur.jh) ? cur.sh : cur.sl);
-            const int ixa = floor_magic(fmaf(cos_approx(tha), rsa, cur.fx));
-            const int iya = floor_magic(fmaf(sin_approx(tha), rsa, cur.fy));
-            const int ixb = floor_magic(fmaf(cos_approx(thb), rsb, cur.fx));
-            const int iyb = floor_magic(fmaf(sin_approx(thb), rsb, cur.fy));
-            const bool ina = (unsigned)ixa < nx && (unsigned)iya < ny;
-            const bool inb = (unsigned)ixb < nx && (unsigned)iyb < ny;
-            // branch-free increments: an electron outside the accepted range adds to a
-            // spare shared word instead (never read), so the common case has no branch
-            red_shared_inc(ina ? tile_acc + (uint32_t)(iya * (TW * 4) + ixa * 4) : dump);
-            red_shared_inc((inb && two) ? tile_acc + (uint32_t)(iyb * (TW * 4) + ixb * 4) : dump);
-            if (!ina || (two && !inb)) { // rare: electrons that left the tile
+            // the unit's width and how many of its four electrons exist
+            const bool wide = j < cur.uh;
+            const float sg = wide ? cur.sh : cur.sl;
+            const int rem = (wide ? cur.nh : cur.nlx) - 4 * j;
+            float u1[4] = {throw_u1(r.x), throw_u1(r.y), throw_u1(r.z), throw_u1(r.w)};
+            if (min(min(r.x, r.y), min(r.z, r.w)) < WB_TAIL_WORD) { // 1e-3 of the units: refine the tail
+                const uint4 t = philox4x32_rounds2to10_fixed(
+                    make_uint4(r1x, r1y, pjh ^ cwk ^ (WB_STREAM_PHOTONS ^ WB_STREAM_PHOTON_TAIL), pjl));
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h ? (!two || inb) : ina)
-                        continue;
-                    const int xa = (h ? ixb : ixa) + ax0, ya = (h ? iyb : iya) + ay0;
-                    if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
-                        if (DIRECT)
-                            deposit(ga, ds, xa, ya, 1);
-                        else
-                            to_window(a, s_local, wox, woy, xa, ya);
+                for (int h = 0; h < 4; ++h)
+                    if (word_of(r, h) < WB_TAIL_WORD)
+                        u1[h] = throw_u1_tail(word_of(r, h), word_of(t, h));
+            }
+            // two pairs of electrons in straight-line code (their MUFU chains interleave).
+            // Branch-free increments: an electron outside the accepted range adds to a spare
+            // shared word (dump, never read), one that does not exist to the next word
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                int ix[2], iy[2];
+                uint32_t ad[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int h = 2 * pr + e;
+                    float dx, dy;
+                    throw_offsets(u1[h], word_of(r, h), sg, dx, dy);
+                    ix[e] = floor_magic(dx + cur.fx);
+                    iy[e] = floor_magic(dy + cur.fy);
+                    const bool in = (unsigned)ix[e] < nx && (unsigned)iy[e] < ny;
+                    ad[e] = in ? tile_acc + (uint32_t)(iy[e] * (TW * 4) + ix[e] * 4) : dump;
+                    if (h > 0)
+                        ad[e] = (rem > h) ? ad[e] : dump + 4;
+                    red_shared_inc(ad[e]);
+                }
+                if (ad[0] == dump || ad[1] == dump) { // rare: electrons that left the tile
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (ad[e] != dump)
+                            continue;
+                        const int xa = ix[e] + ax0, ya = iy[e] + ay0;
+                        if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
+                            if (DIRECT)
+                                deposit(ga, ds, xa, ya, 1);
+                            else
+                                to_window(a, s_local, wox, woy, xa, ya);
+                        }
                     }
                 }
             }
