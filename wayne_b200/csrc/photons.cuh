@@ -266,13 +266,14 @@ __device__ __forceinline__ float throw_theta(uint32_t w) // in (-pi, pi)
 {
     return fmaf(lo16_biased(w) - 8421376.0f, 9.587379924285257e-05f, 4.793689962142629e-05f);
 }
-// offsets of one electron in units of its PSF sigma (radius * cos, radius * sin)
-__device__ __forceinline__ void throw_offsets(float u1, uint32_t w, float sigma, float &dx, float &dy)
+// position of one electron thrown from (cx, cy): centre + sigma sqrt(-2 ln u1) (cos, sin)(theta)
+__device__ __forceinline__ void throw_position(float u1, uint32_t w, float sigma, float cx, float cy,
+                                               float &x, float &y)
 {
-    const float rs = sqrt_approx(-1.3862943611198906f * lg2_approx(u1)) * sigma; // sqrt(-2 ln u1) sigma
+    const float rs = sqrt_approx(-1.3862943611198906f * lg2_approx(u1)) * sigma;
     const float th = throw_theta(w);
-    dx = cos_approx(th) * rs;
-    dy = sin_approx(th) * rs;
+    x = fmaf(cos_approx(th), rs, cx);
+    y = fmaf(sin_approx(th), rs, cy);
 }
 __device__ __forceinline__ uint32_t word_of(const uint4 &r, int i)
 {
@@ -437,13 +438,13 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
                         break;
                     const uint32_t wd = word_of(r, h);
                     const float u1 = (wd < WB_TAIL_WORD) ? throw_u1_tail(wd, word_of(t, h)) : throw_u1(wd);
-                    float dx, dy;
-                    throw_offsets(u1, wd, sg, dx, dy);
+                    float px, py;
+                    throw_position(u1, wd, sg, ux, uy, px, py);
                     // floor on tile-relative coordinates == the reference's (int)
                     // truncation on frame coordinates for every accepted electron
                     // (x in (-1,1) is rejected either way by the strict 0 < x test)
-                    const int ix = __float2int_rd(dx + ux);
-                    const int iy = __float2int_rd(dy + uy);
+                    const int ix = __float2int_rd(px);
+                    const int iy = __float2int_rd(py);
                     if (ix >= T.lox && ix < T.hix && iy >= T.loy && iy < T.hiy) {
                         atomicAdd(&tile[iy * TW + ix], 1);
                     } else {
@@ -588,8 +589,11 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
         }
     }
     const long long q = __double2ll_rn(v * WB_ACC_SCALE);
-    atomicAdd((unsigned long long *)(d.acc + (size_t)(ya + ga.border) * ga.F + (xa + ga.border)),
-              (unsigned long long)q);
+    // (the plane pointer comes out of shared memory: say that it is a global address, or the
+    // compiler emits a generic atomic with a shared-memory CAS path)
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(d.acc + (size_t)(ya + ga.border) * ga.F + (xa + ga.border)),
+                 "l"(q)
+                 : "memory");
 }
 
 #ifndef WB_THROW_MIN_BLOCKS
@@ -679,8 +683,11 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     const unsigned nx = (unsigned)max(0, min(TW, a.nr - tx0) - lox);
     const unsigned ny = (unsigned)max(0, min(TH, a.nc - ty0) - loy);
     int wox = 0, woy = 0;
-    DirectSample ds;
-    if (DIRECT) {
+    // the sub-sample's flat-field / accumulation constants are CTA-uniform and only used by
+    // the flush and by electrons that leave the tile: shared memory, not registers
+    __shared__ DirectSample s_ds;
+    DirectSample &ds = s_ds;
+    if (DIRECT && threadIdx.x == 0) {
         const double *t = a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE;
         ds.g.ox = ds.g.oy = ds.g.s = ds.g.pad = 0;
         ds.g.x_ref = t[0];
@@ -694,10 +701,15 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         while (r + 1 < ga.n_reads && ga.d_read_end[r] < (int)s_glob)
             ++r;
         ds.acc = reinterpret_cast<long long *>(ga.d_acc) + (size_t)r * ga.F * ga.F;
-    } else {
+    }
+    if (!DIRECT) {
         wox = a.d_win_ox[s_local];
         woy = a.d_win_oy[s_local];
     }
+    __shared__ int s_next; // next 32-bin group to hand out (dynamic: counts are ragged)
+    if (threadIdx.x == 0)
+        s_next = 0;
+    __syncthreads();
     BinPar *mybins = s_bin[warp];
     // bin positions are staged relative to the ACCEPTED origin (tx0+lox, ty0+loy),
     // so one unsigned compare per axis is the whole bounds test, and the tile cell
@@ -710,7 +722,13 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     const uint32_t cwk = pin_reg((keys.hw ^ WB_STREAM_PHOTONS) ^ WB_TK1);
 
     const int ngroups = (w1 - w0 + 31) >> 5;
-    for (int g = warp; g < ngroups; g += nwarps) {
+    for (;;) {
+        int g = 0;
+        if (lane == 0)
+            g = atomicAdd(&s_next, 1);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= ngroups)
+            break;
         const int wb = w0 + (g << 5);
         const int w = wb + lane;
         BinPar bp;
@@ -795,29 +813,30 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             const bool wide = j < cur.uh;
             const float sg = wide ? cur.sh : cur.sl;
             const int rem = (wide ? cur.nh : cur.nlx) - 4 * j;
-            float u1[4] = {throw_u1(r.x), throw_u1(r.y), throw_u1(r.z), throw_u1(r.w)};
-            if (min(min(r.x, r.y), min(r.z, r.w)) < WB_TAIL_WORD) { // 1e-3 of the units: refine the tail
-                const uint4 t = philox4x32_rounds2to10_fixed(
-                    make_uint4(r1x, r1y, pjh ^ cwk ^ (WB_STREAM_PHOTONS ^ WB_STREAM_PHOTON_TAIL), pjl));
-#pragma unroll
-                for (int h = 0; h < 4; ++h)
-                    if (word_of(r, h) < WB_TAIL_WORD)
-                        u1[h] = throw_u1_tail(word_of(r, h), word_of(t, h));
-            }
             // two pairs of electrons in straight-line code (their MUFU chains interleave).
             // Branch-free increments: an electron outside the accepted range adds to a spare
             // shared word (dump, never read), one that does not exist to the next word
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) {
+                const uint32_t wa = word_of(r, 2 * pr), wb2 = word_of(r, 2 * pr + 1);
+                float u1[2] = {throw_u1(wa), throw_u1(wb2)};
+                if (min(wa, wb2) < WB_TAIL_WORD) { // 5e-4 of the pairs: refine the far tail
+                    const uint4 t = philox4x32_rounds2to10_fixed(
+                        make_uint4(r1x, r1y, pjh ^ cwk ^ (WB_STREAM_PHOTONS ^ WB_STREAM_PHOTON_TAIL), pjl));
+                    if (wa < WB_TAIL_WORD)
+                        u1[0] = throw_u1_tail(wa, word_of(t, 2 * pr));
+                    if (wb2 < WB_TAIL_WORD)
+                        u1[1] = throw_u1_tail(wb2, word_of(t, 2 * pr + 1));
+                }
                 int ix[2], iy[2];
                 uint32_t ad[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int h = 2 * pr + e;
-                    float dx, dy;
-                    throw_offsets(u1[h], word_of(r, h), sg, dx, dy);
-                    ix[e] = floor_magic(dx + cur.fx);
-                    iy[e] = floor_magic(dy + cur.fy);
+                    float px, py;
+                    throw_position(u1[e], e ? wb2 : wa, sg, cur.fx, cur.fy, px, py);
+                    ix[e] = floor_magic(px);
+                    iy[e] = floor_magic(py);
                     const bool in = (unsigned)ix[e] < nx && (unsigned)iy[e] < ny;
                     ad[e] = in ? tile_acc + (uint32_t)(iy[e] * (TW * 4) + ix[e] * 4) : dump;
                     if (h > 0)
