@@ -16,7 +16,7 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
-def _poisson_draws(lam, n_samples=256, n_bins=4096, key=(7, 9)):
+def _poisson_draws(lam, n_samples=256, n_bins=4096, key=(7, 9), dur_scale=None, flat=True):
     import torch
     from wayne_b200 import _lib
     dev = torch.device('cuda', 0)
@@ -24,6 +24,8 @@ def _poisson_draws(lam, n_samples=256, n_bins=4096, key=(7, 9)):
     one = torch.ones((n_bins,), dtype=torch.float64, device=dev)
     dwl = torch.full((n_bins,), 1e-4, dtype=torch.float64, device=dev)     # x 1e4 -> 1
     dur = torch.full((n_samples,), 1000.0, dtype=torch.float64, device=dev)  # x 1e-3 -> 1
+    if dur_scale is not None:
+        dur = dur * torch.as_tensor(np.asarray(dur_scale, dtype=np.float64), device=dev)
     counts = torch.empty((n_samples, n_bins), dtype=torch.int32, device=dev)
     totals = torch.empty((n_samples,), dtype=torch.int64, device=dev)
     _lib.check(_lib.lib.wb200_counts(n_samples, n_bins, _p(f), None, 0, _p(one), _p(dwl), _p(dur), 1.0,
@@ -31,7 +33,7 @@ def _poisson_draws(lam, n_samples=256, n_bins=4096, key=(7, 9)):
                                      None), 'wb200_counts')
     c = counts.cpu().numpy()
     assert np.array_equal(c.sum(axis=1), totals.cpu().numpy())
-    return c.ravel()
+    return c.ravel() if flat else c
 
 
 @pytest.mark.parametrize("lam", [0.05, 0.7, 3.0, 9.99, 10.0, 14.7, 39.9, 40.0, 60.0, 243.0, 4000.0, 2.5e5])
@@ -209,3 +211,41 @@ def test_native_reads_equal_generic_fast_kernel(monkeypatch):
     monkeypatch.setenv('WB200_GENERIC_READS', '1')
     old = _reads_noise_only(**sky_only)
     assert np.array_equal(new, old)
+
+
+@pytest.mark.parametrize("lam", [0.4, 7.0, 59.0, 99.0])
+def test_count_window_sampler_with_drifting_and_jumping_means(lam):
+    """k_counts_window re-uses one tabulated CDF window over neighbouring sub-samples of a
+    bin (window draw + a Poisson draw of the remainder) and rebuilds it when the mean
+    leaves [lam_t, lam_t + 0.25]: means that drift both ways by parts in 1e4 (a transit in
+    progress) and means that jump by 50 % between sub-samples keep the exact pmf."""
+    n_s = 256
+    drift = 1.0 + 2e-4 * np.sin(np.arange(n_s) / 7.0)
+    c = _poisson_draws(lam, n_s, 4096, key=(31, 32), dur_scale=drift, flat=False)
+    chi2, dof = _chi2_poisson(c.ravel(), lam)            # pooled: all means within 2e-4 of lam
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+    m = c.mean(axis=1)
+    assert np.abs(m - lam * drift).max() < 5.5 * np.sqrt(lam / 4096)
+    jump = np.where(np.arange(n_s) % 2 == 0, 1.0, 1.5)
+    c = _poisson_draws(lam, n_s, 4096, key=(33, 34), dur_scale=jump, flat=False)
+    for par, mult in ((0, 1.0), (1, 1.5)):
+        chi2, dof = _chi2_poisson(c[par::2].ravel(), lam * mult)
+        assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (par, chi2, dof)
+    # neighbouring sub-samples of one bin share a Philox call (different words): independent
+    a, b = c[0::2].ravel().astype(float), c[1::2].ravel().astype(float)
+    assert abs(np.corrcoef(a, b)[0, 1]) < 5 / np.sqrt(a.size)
+
+
+def test_count_window_sampler_tails():
+    """Draws that leave the tabulated window (below lam - 3.7 sigma, above its 64th term)
+    are finished by the recurrence: 64 M draws at lam = 59 reproduce the far-tail masses."""
+    lam = 59.0
+    lo_k, hi_k = 32, 90                      # P(X <= 32) = 8.8e-5, P(X >= 90) = 1.05e-4; the window is [29, 93)
+    n_lo = n_hi = n = 0
+    for key in range(16):
+        x = _poisson_draws(lam, 1024, 4096, key=(41, key))
+        n += x.size
+        n_lo += int((x <= lo_k).sum())
+        n_hi += int((x >= hi_k).sum())
+    for got, p in ((n_lo, stats.poisson.cdf(lo_k, lam)), (n_hi, stats.poisson.sf(hi_k - 1, lam))):
+        assert abs(got - n * p) < 5 * np.sqrt(n * p) + 0.01 * n * p, (got, n * p)

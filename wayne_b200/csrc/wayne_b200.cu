@@ -18,6 +18,7 @@
 #include "reads.cuh"
 #include "reads_native.cuh"
 #include "stage1.cuh"
+#include "counts_native.cuh"
 
 namespace wb {
 thread_local char g_err[512] = "";
@@ -201,6 +202,17 @@ int wb200_counts_ex(const wb200_counts_args *a, void *stream)
                "Chebyshev planet signal: need x and 1 <= order <= 32");
     cudaStream_t st = (cudaStream_t)stream;
     WB_CUDA(cudaMemsetAsync(a->d_totals, 0, sizeof(uint64_t) * a->n_samples, st));
+    if (a->count_mode == WB200_COUNT_POISSON && !getenv("WB200_GENERIC_COUNTS")) {
+        // native mode: CDF-window sampler, a thread owns a bin for CW_BLOCK sub-samples
+        static_assert(CW_BLOCK % 2 == 0, "Philox words are shared by sub-sample pairs");
+        dim3 wgrid((a->n_bins + CW_THREADS - 1) / CW_THREADS, (a->n_samples + CW_BLOCK - 1) / CW_BLOCK);
+        k_counts_window<<<wgrid, CW_THREADS, sizeof(float) * CW_T * CW_THREADS, st>>>(
+            a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld, a->d_cheb_coef,
+            a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl, a->d_dur_ms, a->scale, a->key0, a->key1,
+            a->d_expected, a->d_counts, (unsigned long long *)a->d_totals);
+        WB_LAUNCHED("k_counts_window");
+        return WB200_OK;
+    }
     dim3 grid((a->n_bins + COUNTS_THREADS - 1) / COUNTS_THREADS, (a->n_samples + COUNTS_SPT - 1) / COUNTS_SPT);
     k_counts<<<grid, COUNTS_THREADS, 0, st>>>(a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld,
                                    a->d_cheb_coef, a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl,
