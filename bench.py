@@ -476,19 +476,22 @@ def run_native(args, wk):
     reads_bytes = (R * F * F * 8            # interval accumulators
                    + 2 * R * F * F * 8      # dark, dark error
                    + 2 * F * F * 8          # sky, gain
-                   + 7 * F * F * 8          # non-linearity planes
+                   + 4 * F * F * 8          # non-linearity planes (1+c1, c2, c3, c4; the derivative's
+                                            # coefficients are formed from them in the native kernel)
                    + (F * F * 8 if S == 256 else 0) + F * F * 4   # zero read, cosmic heads
                    + (R + 1) * F * F * 8)   # NSAMP reads written
     t_reads, t_throw, t_gather, t_counts = per('k_reads'), per('k_throw'), per('k_gather'), per('k_counts')
     ww, wh, chunk = geom
     gather_bytes = N * ww * wh * 4 + 2 * R * F * F * 8     # only on the window/gather (parity) path
-    roof_hbm = {'kernel': 'k_reads<0>', 'bound': 'hbm', 'achieved': reads_bytes / (t_reads * 1e-3) / 1e9,
+    roof_hbm = {'kernel': 'k_reads_native', 'bound': 'hbm', 'achieved': reads_bytes / (t_reads * 1e-3) / 1e9,
                 'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': peak_src,
                 'frac': reads_bytes / (t_reads * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
                 'algorithmic_bytes': reads_bytes, 'ms': t_reads}
     # measured denominators for the photon kernel (no memory traffic to speak of):
-    #   mb(7)  Philox4x32-10 + fp32 Box-Muller per electron and nothing else -- the
-    #          issue-slot ceiling of GENERATING electrons on this GPU
+    #   mb(7)  the thrower's random recipe and nothing else (one Philox4x32-10 call + four
+    #          fp32 SFU Box-Muller pairs) -- the ceiling of GENERATING electrons on this GPU
+    #   mb(6)  the Philox4x32-10 calls alone; mb(8) IMAD.WIDE.U32 alone (quarter rate on B200:
+    #          20 of them bound a call at ~80 cycles per warp)
     #   mb(2)  shared-memory atomics with the PSF's 3x3 same-address pattern
     #   mb(1)  conflict-free shared-memory atomics
     import ctypes as C
@@ -500,8 +503,9 @@ def run_native(args, wk):
 
     try:
         rng_peak, atom_psf, atom_free = microbench(7, 2048), microbench(2, 4096), microbench(1, 4096)
+        philox_calls, imad_wide = microbench(6, 2048), microbench(8, 2048)
     except Exception:      # noqa: BLE001
-        rng_peak = atom_psf = atom_free = None
+        rng_peak = atom_psf = atom_free = philox_calls = imad_wide = None
     traffic = {}
     try:
         with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
@@ -511,10 +515,13 @@ def run_native(args, wk):
     roof_hbm['traffic'] = traffic.get('k_reads')
     roof_hbm['traffic_source'] = traffic.get('source')
     roof_throw = {'kernel': 'k_throw_philox (direct accumulation)',
-                  'bound': 'sm_issue: Philox4x32-10 + Box-Muller + shared-memory atomic per electron (HBM idle)',
+                  'bound': 'sm_issue: one Philox4x32-10 call per four electrons (IMAD.WIDE pipe) + SFU Box-Muller + '
+                           'shared-memory atomic per electron (HBM idle)',
                   'achieved': photons / (t_throw * 1e-3) / 1e9, 'peak': rng_peak,
                   'unit': 'Gelectron/s',
-                  'peak_source': 'wb200_microbench(7): Philox4x32-10 + fp32 Box-Muller only, all SMs, this run',
+                  'peak_source': 'wb200_microbench(7): the thrower\'s random recipe only (Philox4x32-10 call + 4 fp32 '
+                                 'SFU Box-Muller pairs), all SMs, this run',
+                  'philox_calls_gcalls_s': philox_calls, 'imad_wide_gops_s': imad_wide,
                   'frac': (photons / (t_throw * 1e-3) / 1e9 / rng_peak) if rng_peak else None,
                   'smem_atomic_peaks_gops': {'psf_like_3x3': atom_psf, 'conflict_free': atom_free},
                   'mufu_bound_gelectron_s': (148 * 16 * (clocks['sm_mhz'] if clocks and clocks.get('sm_mhz')

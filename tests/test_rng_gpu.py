@@ -249,3 +249,60 @@ def test_count_window_sampler_tails():
         n_hi += int((x >= hi_k).sum())
     for got, p in ((n_lo, stats.poisson.cdf(lo_k, lam)), (n_hi, stats.poisson.sf(hi_k - 1, lam))):
         assert abs(got - n * p) < 5 * np.sqrt(n * p) + 0.01 * n * p, (got, n * p)
+
+
+def test_photon_2d_cell_probabilities_narrow_psf():
+    """The thrower's electrons (four per Philox call: 16-bit radius and angle fields, far tail
+    refined from a second call) against the exact cell probabilities of a narrow double
+    Gaussian -- sigma = 0.55 / 1.9 px, the regime of the real PSF -- at 5e7 electrons:
+    chi-square over every cell with >= 200 expected, and the x / y marginals."""
+    from wayne_b200 import pyparallel
+    n = 50_000_000
+    sig_l, sig_h, ratio = 0.55, 1.9, 0.3
+    x0, y0 = 100.37, 90.81
+    frame = pyparallel.psf_frame([n], [x0], [y0], [ratio], [sig_l], [sig_h], 200, 200, test=99,
+                                 rng='philox').astype(float)
+    assert frame.sum() == n
+    k = np.arange(201)
+    nh = int(n * ratio)
+
+    def cells(sig):
+        px = np.diff(stats.norm.cdf(k, x0, sig))
+        py = np.diff(stats.norm.cdf(k, y0, sig))
+        return np.outer(py, px)                      # frame[y, x]
+    exp = nh * cells(sig_h) + (n - nh) * cells(sig_l)
+    sel = exp >= 200
+    chi2 = ((frame[sel] - exp[sel]) ** 2 / exp[sel]).sum()
+    dof = sel.sum() - 1
+    assert dof > 150
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
+    for axis in (0, 1):
+        o, e = frame.sum(axis=axis), exp.sum(axis=axis)
+        s1 = e >= 200
+        c2 = ((o[s1] - e[s1]) ** 2 / e[s1]).sum()
+        assert c2 < s1.sum() + 6 * np.sqrt(2 * s1.sum()), (axis, c2)
+
+
+def test_photon_far_tail_and_isotropy():
+    """Radius fields below 16 (beyond 4.08 sigma) take their radius uniform from a second
+    Philox call: the marginal tail masses beyond 3.5 / 4.5 / 5.2 sigma match the normal
+    law (6.4e7 electrons), and the octants around the centre hold equal counts."""
+    from wayne_b200 import pyparallel
+    n, sig = 64_000_000, 20.0
+    c0 = 507.0                                       # on a pixel corner: the octants are mirror images
+    frame = pyparallel.psf_frame([n], [c0], [c0], [0.0], [sig], [sig], 1014, 1014, test=7,
+                                 rng='philox').astype(float)
+    assert frame.sum() == n
+    for axis in (0, 1):
+        prof = frame.sum(axis=axis)
+        for z in (3.5, 4.5, 5.2):
+            lo, hi = int(np.floor(c0 - z * sig)), int(np.ceil(c0 + z * sig))
+            got = prof[:lo].sum() + prof[hi:].sum()
+            p = stats.norm.cdf(lo, c0, sig) + stats.norm.sf(hi, c0, sig)
+            assert abs(got - n * p) < 5 * np.sqrt(n * p), (axis, z, got, n * p)
+    yy, xx = np.mgrid[0:1014, 0:1014]
+    dx, dy = xx + 0.5 - c0, yy + 0.5 - c0            # pixel centres
+    octant = (dx > 0).astype(int) + 2 * (dy > 0) + 4 * (np.abs(dx) > np.abs(dy))
+    diag = np.abs(dx) == np.abs(dy)
+    tot = np.array([frame[(octant == o) & ~diag].sum() for o in range(8)])
+    assert np.abs(tot - tot.mean()).max() < 5 * np.sqrt(tot.mean()), tot

@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
+#include "photons.cuh"
 
 namespace wb {
 
@@ -102,21 +103,28 @@ __global__ void __launch_bounds__(256) k_mb_pipe(int iters, int *sink)
         sink[0] = 1;
 }
 
-// Philox + fp32 Box-Muller pair, no memory: the ALU/SFU ceiling per electron
+// The thrower's random recipe and nothing else (no bins, no tile, no atomics): the ceiling
+// of GENERATING electron positions on this GPU.
+//   which 6: Philox4x32-10 calls only (fixed key, as in the thrower)
+//   which 7: one call + four electrons (16-bit radius / angle fields, ftz SFU Box-Muller)
 __global__ void __launch_bounds__(256) k_mb_rng(int which, int iters, int *sink)
 {
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     float accf = 0.f;
     uint32_t acci = 0;
+    const ThrowKeys k = throw_keys(0x1234u, 0x5678u);
     for (int it = 0; it < iters; ++it) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)it, t, 7u, 2u), 0x1234u, 0x5678u);
+        const uint4 r = philox4x32_10_throw((uint32_t)it, 7u, t, k);
         if (which == 6) {
             acci ^= r.x ^ r.y ^ r.z ^ r.w;
         } else {
-            float a, b, c, d;
-            box_muller_f(r.x, r.y, a, b);
-            box_muller_f(r.z, r.w, c, d);
-            accf += a + b + c + d;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint32_t w = word_of(r, h);
+                float x, y;
+                throw_position(throw_u1(w), w, 1.25f, 3.0f, 4.0f, x, y);
+                accf += x + y;
+            }
         }
     }
     if (accf == 1.2345f || acci == 0x7fffffffu)

@@ -12,9 +12,9 @@
 
 #include "common.cuh"
 #include "gather.cuh"
-#include "microbench.cuh"
 #include "philox.cuh"
 #include "photons.cuh"
+#include "microbench.cuh"
 #include "reads.cuh"
 #include "reads_native.cuh"
 #include "stage1.cuh"
@@ -557,7 +557,7 @@ int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
     *ms_out = best;
     double ops = (double)blocks * 256.0 * iters;
     if (which == 7)
-        ops *= 2.0; // two electrons (normal pairs) per Philox call
+        ops *= 4.0; // four electrons per Philox call
     if (which >= 8)
         ops *= 64.0; // probed instructions per iteration and thread
     *ops_out = ops;
