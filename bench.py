@@ -561,7 +561,7 @@ def run_native(args, wk):
                     'achieved_gbs': gather_bytes / (t_gather * 1e-3) / 1e9} if t_gather else None),
     }
     if world == 1 and not args.no_cpu:
-        sec, info = cpu_reference_exposure(wk, inp, 16 * len(inp['read_index']))   # ~10-15 s of CPU work
+        sec, info = cpu_reference_exposure(wk, inp, 48 * len(inp['read_index']))   # ~10-15 s of CPU work
         line['cpu_baseline'] = {'value': 1.0 / sec, 'unit': 'exposures/s', 'cores': info['cores'],
                                 'kind': info['kind'], 'sample': info['sample'],
                                 'photons_per_s': info['photons_per_exposure'] / sec,
