@@ -22,14 +22,15 @@
 //   warp  = takes 32 consecutive bins; a warp-level prefix sum of their work
 //           units turns the ragged "counts[bin] electrons per bin" loop into a
 //           dense stream of units (load balance is exact whatever the counts).
-//   unit  = PHILOX: one Philox4x32-10 call = 2 electrons of one bin
+//   unit  = PHILOX: one Philox4x32-10 call = up to 4 electrons of one width of one bin
 //           RANDR / HOST: one electron (fp64, bit-compatible with the reference)
 //   bin   = shared-memory atomic add into the tile; electrons that leave the
 //           tile but not the frame go straight to HBM (rare: |z| > ~4).  At the
 //           end the tile is flushed with integer atomics -- integer adds
 //           commute, so the result is deterministic.
 //   HBM traffic per electron is ~0 by construction; the stage is bound by issue
-//   slots for RNG + Box-Muller (measured: profiles/), not by the atomics.
+//   slots for RNG + Box-Muller -- the quarter-rate IMAD.WIDE of the Philox rounds first
+//   of all (measured: profiles/r01_pipe_rates_s3.txt) -- not by the atomics.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -521,20 +522,22 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
 
 // ---------------------------------------------------------------------------
 // Native (Philox) electron thrower, written for instruction count: the
-// baseline generic kernel above spends 111 warp-instructions per 32 electrons
-// (profiles/r01_k_throw_opcode_histogram_baseline.txt); most of them are the
-// per-unit shuffle binary search, the per-round Philox key bumps and the IEEE
-// sqrt / F2I sequences.  Here
-//   * a lane owns a contiguous RUN of units of its warp's 32-bin group: one
-//     binary search per lane and group, then a sequential walk that only steps
-//     to the next bin when its units are exhausted (bin parameters live in
-//     shared memory, 32 B per bin) -- no warp collectives in the hot loop;
-//   * the 20 Philox round keys are kernel parameters (constant-bank operands);
+// baseline generic kernel above spent 111 warp-instructions per 32 electrons
+// (profiles/r01_k_throw_opcode_histogram_baseline.txt), this one 64
+// (profiles/r01_k_throw_opcodes_s3.txt).  Here
+//   * a warp takes its 32-bin groups from a shared counter; a lane owns a contiguous
+//     RUN of units of the group: one binary search per lane and group, then a
+//     sequential walk that only steps to the next bin when its units are exhausted
+//     (bin parameters live in shared memory, 32 B per bin) -- no warp collectives
+//     in the hot loop;
+//   * the Philox key is fixed (round keys are immediates), the bin's half of round 1
+//     is cached, and one call feeds FOUR electrons (see "one Philox call" above);
 //   * sqrt.approx / lg2.approx / sin.approx / cos.approx (4 MUFU per electron),
-//     floor by the round-down magic-number add (FADD.RM, no F2I on the XU pipe);
-//   * tile-relative unsigned bounds tests.
-// Same counters as the generic kernel -- (pair index, bin, sample, stream) -- so
-// a given key throws the same electrons whatever the launch geometry.
+//     PRMT field extraction (no I2F), floor by the round-down magic-number add
+//     (FADD.RM, no F2I on the XU pipe);
+//   * tile-relative unsigned bounds tests and branch-free shared increments.
+// Same counters as the generic kernel's PHILOX path -- (unit, sub-sample, bin,
+// stream) -- so a given key throws the same electrons whatever the launch geometry.
 // ---------------------------------------------------------------------------
 // keeps a CTA-uniform value in a vector register instead of letting ptxas rebuild it
 // from the kernel parameters every iteration
