@@ -38,7 +38,8 @@ from ._lib import lib, check
 
 BORDER = 5
 TILE_W, TILE_H = 128, 64            # must match csrc/wayne_b200.cu
-ZMAX = {_lib.RNG_PHILOX: 6.8, _lib.RNG_RANDR: 6.6}
+# largest |z| a stream can produce: the native thrower reaches sqrt(2*49*ln 2) = 8.24 (photons.cuh), rand_r 6.6
+ZMAX = {_lib.RNG_PHILOX: 8.3, _lib.RNG_RANDR: 6.6}
 WINDOW_BYTES_CAP = 2 << 30          # HBM spent on sub-sample windows per batch
 
 
