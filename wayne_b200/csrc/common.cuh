@@ -38,6 +38,20 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
                             cudaGetErrorString(e__));                          \
     } while (0)
 
+// Device-side index checks of the bounds-checked build (-DWB_BOUNDS_CHECK, see
+// tools/bounds_check_build.py: compute-sanitizer is not available on the GPU pool).  A failed
+// check traps, which the next CUDA call reports as an error, so a test run under that build
+// fails loudly.  Compiled out of the product build.
+#ifdef WB_BOUNDS_CHECK
+#define WB_DEV_ASSERT(cond)                                                    \
+    do {                                                                       \
+        if (!(cond))                                                           \
+            __trap();                                                          \
+    } while (0)
+#else
+#define WB_DEV_ASSERT(cond) ((void)0)
+#endif
+
 #define WB_REQUIRE(cond, msg)                                                  \
     do {                                                                       \
         if (!(cond))                                                           \

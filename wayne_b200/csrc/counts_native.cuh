@@ -113,9 +113,12 @@ __device__ __forceinline__ int count_window_draw(const float *tbl, const CountWi
     }
     int j = 0; // entries < u; tbl[CW_T-1] >= u
 #pragma unroll
-    for (int step = CW_T / 2; step >= 1; step >>= 1)
+    for (int step = CW_T / 2; step >= 1; step >>= 1) {
+        WB_DEV_ASSERT(j + step - 1 >= 0 && j + step - 1 < CW_T);
         if (tbl[(j + step - 1) * CW_THREADS] < u)
             j += step;
+    }
+    WB_DEV_ASSERT(j < CW_T && tbl[j * CW_THREADS] >= u);
     return t.k0 + j;
 }
 
@@ -207,6 +210,7 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
                 if (c > 2147483647LL)
                     c = 2147483647LL; // the reference's counters are 32-bit (pyparallel_menu.c:12)
             }
+            WB_DEV_ASSERT(c >= 0 && s < N && w < W);
             if (counts)
                 counts[(size_t)s * W + w] = (int)c;
         }

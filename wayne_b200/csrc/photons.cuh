@@ -591,6 +591,7 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
             v *= fv;
         }
     }
+    WB_DEV_ASSERT((unsigned)(ya + ga.border) < (unsigned)ga.F && (unsigned)(xa + ga.border) < (unsigned)ga.F);
     const long long q = __double2ll_rn(v * WB_ACC_SCALE);
     // (the plane pointer comes out of shared memory: say that it is a global address, or the
     // compiler emits a generic atomic with a shared-memory CAS path)
@@ -803,6 +804,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             if (j >= cur.units) {      // rare: step to the next bin that has units
                 do {
                     ++b;
+                    WB_DEV_ASSERT(b < 32);
                     cur = mybins[b];
                 } while (cur.units == 0);
                 j = 0;
@@ -844,6 +846,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                     ad[e] = in ? tile_acc + (uint32_t)(iy[e] * (TW * 4) + ix[e] * 4) : dump;
                     if (h > 0)
                         ad[e] = (rem > h) ? ad[e] : dump + 4;
+                    WB_DEV_ASSERT(ad[e] >= dump - (uint32_t)(TW * TH * 4) && ad[e] <= dump + 4 && (ad[e] & 3) == 0);
                     red_shared_inc(ad[e]);
                 }
                 if (ad[0] == dump || ad[1] == dump) { // rare: electrons that left the tile

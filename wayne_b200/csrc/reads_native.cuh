@@ -105,9 +105,12 @@ __device__ __forceinline__ int sky_window_draw(const float *tbl, const SkyWindow
     // j = number of entries < u (<= SKY_T-1 because tbl[SKY_T-1] >= u)
     int j = 0;
 #pragma unroll
-    for (int step = SKY_T / 2; step >= 1; step >>= 1)
+    for (int step = SKY_T / 2; step >= 1; step >>= 1) {
+        WB_DEV_ASSERT(j + step - 1 >= 0 && j + step - 1 < SKY_T);
         if (tbl[(j + step - 1) * (2 * RN_THREADS)] < u)
             j += step;
+    }
+    WB_DEV_ASSERT(j < SKY_T && tbl[j * (2 * RN_THREADS)] >= u);
     return t.k0 + j;
 }
 
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
     const int Y = (int)(idx / (uint32_t)half);
     const int X = (int)(idx - (uint32_t)Y * (uint32_t)half) * 2;
     const uint32_t p = (uint32_t)Y * (uint32_t)F + (uint32_t)X;
+    WB_DEV_ASSERT(p + 1 < plane && (p & 1) == 0);
     const bool rowin = Y >= B && Y < F - B;
     const bool in0 = rowin && X >= B && X < F - B;
     const bool in1 = rowin && (X + 1) >= B && (X + 1) < F - B;
