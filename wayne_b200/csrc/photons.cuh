@@ -548,11 +548,10 @@ __device__ __forceinline__ uint32_t pin_reg(uint32_t v)
     return r;
 }
 
-struct BinPar {        // 32 bytes, two 128-bit shared loads
-    int units;         // Philox calls of the bin: ceil(nh/4) wide ones, then ceil(nl/4) narrow ones
-    int uh;            // units below uh are wide
-    int nh;            // wide electrons: unit j < uh holds min(4, nh - 4j)
-    int nlx;           // nl + 4*uh: unit j >= uh holds min(4, nlx - 4j)
+struct BinPar {        // 32 bytes, two 128-bit shared loads per trip of the electron loop
+    uint32_t r1x, r1y; // the bin's half of Philox round 1: hi(M1*bin) ^ c.y ^ k0, lo(M1*bin)
+    int nh;            // wide electrons: units j with 4j < nh are wide and hold min(4, nh - 4j)
+    int nlx;           // nl + 4*ceil(nh/4): the other units hold min(4, nlx - 4j); units = ceil(nlx/4)
     float fx, fy, sl, sh;
 };
 
@@ -765,14 +764,18 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             }
         }
         nh = max(0, min(nh, cnt));
-        bp.uh = (nh + 3) >> 2;
-        bp.units = bp.uh + ((cnt - nh + 3) >> 2);
         bp.nh = nh;
-        bp.nlx = cnt - nh + 4 * bp.uh;
-        const int incl = warp_incl_scan(bp.units);
+        bp.nlx = cnt - nh + ((nh + 3) & ~3);
+        const int units = (bp.nlx + 3) >> 2; // ceil(nh/4) wide ones, then ceil(nl/4) narrow ones
+        mul_wide((uint32_t)w, WB_PHILOX_M1, bp.r1y, bp.r1x);
+        bp.r1x ^= cyk;
+        const int incl = warp_incl_scan(units);
         const int total = __shfl_sync(FULL, incl, 31);
+        // bins that have units are staged back to back, so the walk below steps with "+1"
+        const uint32_t have = __ballot_sync(FULL, units > 0);
         __syncwarp();
-        mybins[lane] = bp;
+        if (units > 0)
+            mybins[__popc(have & ((1u << lane) - 1u))] = bp;
         __syncwarp();
         if (total == 0)
             continue;
@@ -788,36 +791,33 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             if (v <= q)
                 b += step;
         }
-        const int excl_b = __shfl_sync(FULL, incl - bp.units, b);
+        const int excl_b = __shfl_sync(FULL, incl - units, b);
         if (q >= qend)
             continue; // (no collectives below)
         // flat walk over the run (all lanes execute the same body every trip; a
         // lane steps to its next bin when the current one has no units left)
-        BinPar cur = mybins[b];
-        int j = q - excl_b;            // unit index inside the current bin (< cur.units here)
+        const BinPar *pb = mybins + __popc(have & ((1u << b) - 1u));
+        int j = q - excl_b;            // unit index inside the current bin
         int n = qend - q;              // units of this lane's run still to do
-        // the bin's half of Philox round 1: (hi(M1*bin) ^ c.y ^ k0, lo(M1*bin))
-        uint32_t r1x, r1y;
-        mul_wide((uint32_t)(wb + b), WB_PHILOX_M1, r1y, r1x);
-        r1x ^= cyk;
+        int units_cur = 0x7fffffff;    // units of the bin pb points at (known after the first load)
         do {
-            if (j >= cur.units) {      // rare: step to the next bin that has units
-                do {
-                    ++b;
-                    WB_DEV_ASSERT(b < 32);
-                    cur = mybins[b];
-                } while (cur.units == 0);
-                j = 0;
-                mul_wide((uint32_t)(wb + b), WB_PHILOX_M1, r1y, r1x);
-                r1x ^= cyk;
-            }
+            // step to the next staged bin when this one is used up, then (re)load the bin:
+            // branch-free -- at four electrons per unit some lane steps on most trips
+            const bool adv = j >= units_cur;
+            pb += adv ? 1 : 0;
+            j = adv ? 0 : j;
+            WB_DEV_ASSERT(pb < mybins + 32);
+            const BinPar cur = *pb;
+            units_cur = (cur.nlx + 3) >> 2;
+            const uint32_t r1x = cur.r1x, r1y = cur.r1y;
             uint32_t pjl, pjh;
             mul_wide((uint32_t)j, WB_PHILOX_M0, pjl, pjh);
             const uint4 r = philox4x32_rounds2to10_fixed(make_uint4(r1x, r1y, pjh ^ cwk, pjl));
             // the unit's width and how many of its four electrons exist
-            const bool wide = j < cur.uh;
+            const int j4 = 4 * j;
+            const bool wide = j4 < cur.nh;
             const float sg = wide ? cur.sh : cur.sl;
-            const int rem = (wide ? cur.nh : cur.nlx) - 4 * j;
+            const int rem = (wide ? cur.nh : cur.nlx) - j4;
             // two pairs of electrons in straight-line code (their MUFU chains interleave).
             // Branch-free increments: an electron outside the accepted range adds to a spare
             // shared word (dump, never read), one that does not exist to the next word
