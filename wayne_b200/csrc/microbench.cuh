@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) k_mb_rng(int which, int iters, int *sink)
             for (int h = 0; h < 4; ++h) {
                 const uint32_t w = word_of(r, h);
                 float x, y;
-                throw_position(throw_u1(w), w, 1.25f, 3.0f, 4.0f, x, y);
+                throw_position(throw_u1(w), w, 1.25f * WB_SQRT_2LN2, 3.0f, 4.0f, x, y);
                 accf += x + y;
             }
         }

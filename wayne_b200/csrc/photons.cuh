@@ -263,15 +263,22 @@ __device__ __forceinline__ float throw_u1_tail(uint32_t w, uint32_t t) // (k + v
     const float v = fmaf((float)t, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     return ((hi16_biased(w) - 8388608.0f) + v) * 1.52587890625e-05f;
 }
-__device__ __forceinline__ float throw_theta(uint32_t w) // in (-pi, pi)
+// angle in (-pi, pi) up to a constant rotation of ~3e-5 rad (the rounding of the two
+// constants; one fused multiply-add, exact product): (t - 32768 + 1/2) 2 pi 2^-16
+__device__ __forceinline__ float throw_theta(uint32_t w)
 {
-    return fmaf(lo16_biased(w) - 8421376.0f, 9.587379924285257e-05f, 4.793689962142629e-05f);
+    // c = 2 pi / 65536 as float; d = -c * (2^23 + 32768) + c / 2, rounded from double
+    return fmaf(lo16_biased(w), 9.58738019107841e-05f, -807.3892822265625f);
 }
-// position of one electron thrown from (cx, cy): centre + sigma sqrt(-2 ln u1) (cos, sin)(theta)
-__device__ __forceinline__ void throw_position(float u1, uint32_t w, float sigma, float cx, float cy,
+// sqrt(2 ln 2): the PSF widths are staged pre-multiplied, so the radius is
+// sigma' * sqrt(-lg2 u1) with no multiply in between
+constexpr float WB_SQRT_2LN2 = 1.1774100225154747f;
+// position of one electron thrown from (cx, cy): centre + sigma sqrt(-2 ln u1) (cos, sin)(theta),
+// sigma_s = sigma * WB_SQRT_2LN2
+__device__ __forceinline__ void throw_position(float u1, uint32_t w, float sigma_s, float cx, float cy,
                                                float &x, float &y)
 {
-    const float rs = sqrt_approx(-1.3862943611198906f * lg2_approx(u1)) * sigma;
+    const float rs = sqrt_approx(-lg2_approx(u1)) * sigma_s;
     const float th = throw_theta(w);
     x = fmaf(cos_approx(th), rs, cx);
     y = fmaf(sin_approx(th), rs, cy);
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
             // tile-relative fp32 copies of the bin parameters
             const float fx = (float)(bx - (double)T.x0);
             const float fy = (float)(by - (double)T.y0);
-            const float fsl = (float)bsl, fsh = (float)bsh;
+            const float fsl = (float)bsl * WB_SQRT_2LN2, fsh = (float)bsh * WB_SQRT_2LN2;
             for (int base = 0; base < total; base += 32) {
                 const int q = base + lane;
                 int b = 0;
@@ -759,6 +766,8 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                     bad = true;
                 if (bad)
                     cnt = 0;
+                bp.sl *= WB_SQRT_2LN2; // see throw_position
+                bp.sh *= WB_SQRT_2LN2;
             } else {
                 cnt = 0;
             }
