@@ -555,6 +555,18 @@ __device__ __forceinline__ uint32_t pin_reg(uint32_t v)
     return r;
 }
 
+// cell address if (ix, iy) lies in the accepted range [0, nx) x [0, ny), else `other`: two chained
+// compares and ONE select (the compiler's own lowering selects once per axis)
+__device__ __forceinline__ uint32_t select_in_range(uint32_t ix, uint32_t nx, uint32_t iy, uint32_t ny,
+                                                    uint32_t cell, uint32_t other)
+{
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\tsetp.lt.and.u32 p, %3, %4, p;\n\tselp.b32 %0, %5, %6, p;\n\t}"
+        : "=r"(r)
+        : "r"(ix), "r"(nx), "r"(iy), "r"(ny), "r"(cell), "r"(other));
+    return r;
+}
+
 struct BinPar {        // 32 bytes, two 128-bit shared loads per trip of the electron loop
     uint32_t r1x, r1y; // the bin's half of Philox round 1: hi(M1*bin) ^ c.y ^ k0, lo(M1*bin)
     int nh;            // wide electrons: units j with 4j < nh are wide and hold min(4, nh - 4j)
@@ -851,8 +863,8 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                     throw_position(u1[e], e ? wb2 : wa, sg, cur.fx, cur.fy, px, py);
                     ix[e] = floor_magic(px);
                     iy[e] = floor_magic(py);
-                    const bool in = (unsigned)ix[e] < nx && (unsigned)iy[e] < ny;
-                    ad[e] = in ? tile_acc + (uint32_t)(iy[e] * (TW * 4) + ix[e] * 4) : dump;
+                    ad[e] = select_in_range((uint32_t)ix[e], nx, (uint32_t)iy[e], ny,
+                                            tile_acc + (uint32_t)(iy[e] * (TW * 4) + ix[e] * 4), dump);
                     if (h > 0)
                         ad[e] = (rem > h) ? ad[e] : dump + 4;
                     WB_DEV_ASSERT(ad[e] >= dump - (uint32_t)(TW * TH * 4) && ad[e] <= dump + 4 && (ad[e] & 3) == 0);
