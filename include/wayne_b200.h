@@ -324,8 +324,15 @@ int wb200_reads(const wb200_reads_args *args, void *stream);
 int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels,
                         int32_t *d_head, int32_t *d_next, void *stream);
 
-/* Microbenchmarks used for the roofline denominators (profiles/): shared-memory
- * atomic and global red rates.  Returns elapsed ms in *ms_out.  Synchronous. */
+/* Microbenchmarks used for the roofline denominators (profiles/).  which:
+ *   0..3  shared-memory atomics (same address / conflict-free / PSF-like 3x3 / random)
+ *   4, 5  global red (spread over 64 MB / hot 256 KB window)
+ *   6     Philox4x32-10 calls of the thrower's fixed-key stream alone
+ *   7     the thrower's whole random recipe (one call + four fp32 SFU Box-Muller pairs)
+ *   8..13 single-instruction issue-rate probes: IMAD.WIDE.U32, IMAD, LOP3, MUFU.LG2,
+ *         FFMA, I2FP
+ * Returns the best elapsed ms of 3 timed launches in *ms_out and the operations per
+ * launch in *ops_out.  Synchronous. */
 int wb200_microbench(int which, int iters, double *ms_out, double *ops_out);
 
 #ifdef __cplusplus
