@@ -201,9 +201,9 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
                     count_window_build(tbl, win, lam * (1.0f - CW_MARGIN));
                     rest = lam - win.lam;
                 }
-                c = count_window_draw(tbl, win, (float)u01d(wu));
+                c = count_window_draw(tbl, win, u01f(wu));
                 if (rest > 0.0f)
-                    c += poisson_inversion_u((float)u01d(wu2), rest);
+                    c += poisson_inversion_u(u01f(wu2), rest);
             } else {
                 PhiloxStream g(k0, k1, (uint32_t)w, (uint32_t)s, WB_STREAM_COUNTS);
                 c = poisson_draw_fast(g, e);
@@ -214,7 +214,13 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
             if (counts)
                 counts[(size_t)s * W + w] = (int)c;
         }
-        const unsigned long long v = warp_sum_u64((unsigned long long)c);
+        // photons of this sub-sample: one hardware warp reduction when every lane's count fits
+        // 26 bits (always, short of a saturated detector), the shuffle tree otherwise
+        unsigned long long v;
+        if (__all_sync(0xffffffffu, c < (1LL << 26)))
+            v = __reduce_add_sync(0xffffffffu, (unsigned)c);
+        else
+            v = warp_sum_u64((unsigned long long)c);
         if (lane_id() == 0 && v)
             atomicAdd(&totals[s], v);
     }
