@@ -103,6 +103,7 @@ class DeviceEngine(object):
         self.device = device
         self._planes = {}
         self._pinned = {}
+        self._pinned_made = {}
         self._marks = []
         self._open = {}
         self._copy_stream = None
@@ -173,7 +174,18 @@ class DeviceEngine(object):
         an Exposure holds are never overwritten by a later exposure."""
         key = (tuple(shape), dtype)
         free = self._pinned.setdefault(key, [])
-        t = free.pop() if free else torch.empty(shape, dtype=dtype, pin_memory=True)
+        if not free:
+            # cudaHostAlloc of a 126 MB buffer takes ~100 ms: a pool that grows one buffer at a
+            # time stalls a pipelined visit whenever the garbage collector returns a buffer a
+            # little late.  The first exposure of a shape gets one buffer; the second one (the
+            # caller is evidently repeating the shape) makes the pool as deep as the pipeline
+            # can get -- exposures in flight plus the ones the caller still holds.
+            made = self._pinned_made.get(key, 0)
+            grow = 1 if made == 0 else max(1, self.PINNED_RESERVE - made)
+            for _ in range(grow):
+                free.append(torch.empty(shape, dtype=dtype, pin_memory=True))
+            self._pinned_made[key] = made + grow
+        t = free.pop()
         arr = t.numpy()
         weakref.finalize(arr, free.append, t)
         return t, arr
@@ -193,6 +205,7 @@ class DeviceEngine(object):
         return out
 
     MAX_IN_FLIGHT = 4      # exposures in flight before the host waits (~1 GB of HBM each)
+    PINNED_RESERVE = 10    # depth of the pinned download pool once a shape repeats (see pinned_out)
 
     def _streams(self):
         if self._copy_stream is None:
