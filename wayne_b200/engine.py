@@ -577,6 +577,10 @@ class ExposureRun(object):
         core = max(8.0, TILE_W - 2.0 * 4.0 * sig)
         chunk = int(self.W * core / extent) if extent > core else self.W
         chunk = max(32, chunk // 32 * 32)
+        # equal chunks: the same number of CTAs per sub-sample, but of equal length (a short last
+        # chunk makes CTAs of very different duration)
+        n_chunks = int(math.ceil(self.W / float(chunk)))
+        chunk = max(32, int(math.ceil(self.W / float(n_chunks) / 32.0)) * 32)
         want_ctas = 148 * 16
         if self.N * math.ceil(self.W / chunk) < want_ctas:
             per = max(1, want_ctas // self.N)
