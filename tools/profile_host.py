@@ -38,8 +38,10 @@ for i in range(3):
 torch.cuda.synchronize()
 pr = cProfile.Profile()
 pr.enable()
-for i in range(5):
+N_PROF = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+for i in range(N_PROF):
     one(10 + i)
 torch.cuda.synchronize()
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(35)
+pstats.Stats(pr).sort_stats('tottime').print_stats(30)

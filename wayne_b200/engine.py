@@ -619,7 +619,12 @@ class ExposureRun(object):
         N, W, L, F = self.N, self.W, self.L, self.F
         self.d_acc = e.zeros((self.R, F, F), torch.int64)
         self.acc_fixed = True
-        _, _, ww, wh, chunk = self._window_geometry(ZMAX[_lib.RNG_PHILOX], stride=max(1, N // 32))
+        # the direct path has no windows: only the bins-per-CTA choice is needed, and it depends on
+        # the trace length and the PSF width, not on this exposure's pointing -- cached per set-up
+        gkey = ("chunk", self.grism.name, self.S, W, N, float(self.wl_host[0]), float(self.wl_host[-1]))
+        geo = e.cached_plane(gkey, lambda: self._window_geometry(ZMAX[_lib.RNG_PHILOX],
+                                                                 stride=max(1, N // 32))[2:])
+        ww, wh, chunk = geo
         self.win_geometry = (ww, wh, chunk)
         pa = _lib.PhotonArgs()
         pa.n_samples, pa.n_bins, pa.chunk_bins = N, W, chunk
