@@ -1,5 +1,10 @@
+"""Issue rates of single instruction kinds and of the thrower's random recipe on the GPU at hand
+(wb200_microbench 6..13): the evidence behind DESIGN.md 4.1b (IMAD.WIDE.U32 at a quarter of the
+issue rate bounds a Philox4x32-10 call at ~80 cycles per warp).  Usage (GPU box):
+    python tools/pipe_rates.py > gpurun_out/pipes.txt"""
 import ctypes as C, sys
-sys.path.insert(0, '.')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 torch.cuda.init(); torch.zeros(1, device='cuda')
 from wayne_b200 import _lib
