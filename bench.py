@@ -531,6 +531,8 @@ def run_native(args, wk):
                   'philox_calls_gcalls_s': philox_calls, 'imad_wide_gops_s': imad_wide,
                   'frac': (photons / (t_throw * 1e-3) / 1e9 / rng_peak) if rng_peak else None,
                   'smem_atomic_peaks_gops': {'psf_like_3x3': atom_psf, 'conflict_free': atom_free},
+                  # one shared-memory increment per in-frame electron
+                  'increments_over_atomic_peak': ((photons / (t_throw * 1e-3) / 1e9 / atom_psf) if atom_psf else None),
                   'mufu_bound_gelectron_s': (148 * 16 * (clocks['sm_mhz'] if clocks and clocks.get('sm_mhz')
                                                         else 1965.0) * 1e6 / 4) / 1e9,
                   'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
