@@ -223,7 +223,11 @@ __device__ __forceinline__ void red_shared_inc(uint32_t addr)
 // with round-toward-minus-infinity leaves floor(v) in the low mantissa bits.
 __device__ __forceinline__ int floor_magic(float v)
 {
+#ifdef WB_FLOOR_F2I
+    return __float2int_rd(v); // A/B variant: conversion on the XU pipe
+#else
     return __float_as_int(__fadd_rd(v, 12582912.0f)) - 0x4B400000;
+#endif
 }
 
 // ---- one Philox call = FOUR electrons --------------------------------------------
