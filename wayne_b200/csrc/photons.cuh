@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
     if (ssum == 0 && a.d_totals)
         return; // nothing to throw in this sub-sample (uniform over the CTA)
 
-    TraceCoef tc;
+    TraceCoef tc = {}; // (read only when the positions come from the trace, but never indeterminate)
     if (!a.d_xpos)
         tc = load_trace(a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE);
     const size_t row = (size_t)s_local * W;
@@ -647,7 +647,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     if (a.d_totals && a.d_totals[s_local] == 0)
         return;
 
-    TraceCoef tc;
+    TraceCoef tc = {}; // (read only when the positions come from the trace, but never indeterminate)
     if (!a.d_xpos)
         tc = load_trace(a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE);
     const size_t row = (size_t)s_local * W;
