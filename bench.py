@@ -32,7 +32,6 @@ exposures (weak scaling, no data-path collective); value = all ranks' exposures
 import argparse
 import json
 import os
-import subprocess
 import sys
 import tempfile
 import time
