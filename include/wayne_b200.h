@@ -335,6 +335,17 @@ int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels,
  * launch in *ops_out.  Synchronous. */
 int wb200_microbench(int which, int iters, double *ms_out, double *ops_out);
 
+/* Test hook: raw words of the library's counter-based random streams, computed on the
+ * device (host pointers in and out; synchronous).
+ *   which = 0: Philox4x32-10 (Salmon et al., SC'11) of counter c[4] under key k[2], the
+ *              function behind the count / per-pixel samplers: the Random123 known-answer
+ *              vectors apply (tests/test_rng_gpu.py);
+ *   which = 1: the native thrower's call for unit c[0] of bin c[2] in sub-sample c[1] of the
+ *              exposure keyed k[2], stream id c[3] (2 electrons, 7 their tail refinement):
+ *              fixed-key Philox4x32-10 over (unit, hy + sub-sample, bin, hw ^ stream) with
+ *              (hy, hw) = splitmix64 of the key; out[4], out[5] return hy, hw. */
+int wb200_philox_words(int which, const uint32_t *c, const uint32_t *k, uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

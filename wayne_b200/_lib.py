@@ -121,6 +121,7 @@ SIGNATURES = {
     "wb200_reads": (c_int, [C.POINTER(ReadsArgs), c_void_p]),
     "wb200_cosmic_chains": (c_int, [c_int, c_void_p, c_i32, c_void_p, c_void_p, c_void_p]),
     "wb200_microbench": (c_int, [c_int, c_int, DP, DP]),
+    "wb200_philox_words": (c_int, [c_int, C.POINTER(c_u32), C.POINTER(c_u32), C.POINTER(c_u32)]),
 }
 
 

@@ -131,4 +131,21 @@ __global__ void __launch_bounds__(256) k_mb_rng(int which, int iters, int *sink)
         sink[0] = 1;
 }
 
+// test hook behind wb200_philox_words
+__global__ void k_philox_words(int which, uint4 c, uint32_t k0, uint32_t k1, uint32_t *out)
+{
+    uint4 r;
+    ThrowKeys tk = throw_keys(k0, k1);
+    if (which == 0)
+        r = philox4x32_10(c, k0, k1);
+    else
+        r = philox4x32_10_throw(c.x, c.y, c.z, tk, c.w);
+    out[0] = r.x;
+    out[1] = r.y;
+    out[2] = r.z;
+    out[3] = r.w;
+    out[4] = tk.hy;
+    out[5] = tk.hw;
+}
+
 } // namespace wb

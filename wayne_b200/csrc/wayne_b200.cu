@@ -507,6 +507,19 @@ int *PSF(int *counts, int size, double *x_pos, double *y_pos, double *psf_ratio,
     return frame;
 }
 
+int wb200_philox_words(int which, const uint32_t *c, const uint32_t *k, uint32_t *out)
+{
+    WB_REQUIRE((which == 0 || which == 1) && c && k && out, "bad args");
+    uint32_t *d = nullptr;
+    WB_CUDA(cudaMalloc(&d, 6 * sizeof(uint32_t)));
+    k_philox_words<<<1, 1>>>(which, make_uint4(c[0], c[1], c[2], c[3]), k[0], k[1], d);
+    WB_LAUNCHED("k_philox_words");
+    const cudaError_t e = cudaMemcpy(out, d, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    WB_CUDA(e);
+    return WB200_OK;
+}
+
 int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
 {
     WB_REQUIRE(which >= 0 && which <= 13 && iters > 0 && ms_out && ops_out, "bad args");
