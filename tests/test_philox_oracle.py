@@ -67,3 +67,45 @@ def test_device_thrower_stream_equals_oracle():
             got = _device_words(1, [unit, sample, b, stream], key)
             assert got[:4] == P.thrower_words(unit, sample, b, key, stream)
             assert tuple(got[4:]) == P.throw_keys(*key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lam", [0.4, 7.0, 59.0])
+def test_count_sampler_is_the_poisson_quantile_of_its_uniforms(lam):
+    """k_counts_window is inversion of ONE uniform per term: with the Philox words restated by
+    the oracle, every drawn count equals  Q(lam_t; u) + Q(lam - lam_t; u2)  (Q = the exact
+    Poisson quantile function, lam_t = the tabulated mean 4.5 % below lam), except where a
+    uniform falls within float32 rounding of a CDF step."""
+    import torch
+    from scipy import stats
+    from wayne_b200 import _lib
+    n_s, n_b, key = 64, 1024, (77, 99)
+    dev = torch.device('cuda', 0)
+    f = torch.full((n_b,), float(lam), dtype=torch.float64, device=dev)
+    one = torch.ones((n_b,), dtype=torch.float64, device=dev)
+    dwl = torch.full((n_b,), 1e-4, dtype=torch.float64, device=dev)
+    dur = torch.full((n_s,), 1000.0, dtype=torch.float64, device=dev)
+    counts = torch.empty((n_s, n_b), dtype=torch.int32, device=dev)
+    totals = torch.empty((n_s,), dtype=torch.int64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())          # noqa: E731
+    _lib.check(_lib.lib.wb200_counts(n_s, n_b, p(f), None, 0, p(one), p(dwl), p(dur), 1.0,
+                                     _lib.COUNT_POISSON, key[0], key[1], None, p(counts), p(totals),
+                                     None), 'wb200_counts')
+    got = counts.cpu().numpy()
+    # the kernel's arithmetic, restated: mean in float64 (same multiplication order), then float32
+    e = np.float64(lam) * 1.0 * 1e-4 * 1e4 * 1000.0 * 1e-3 * 1.0
+    lam32 = np.float32(e)
+    lam_t = np.float32(lam32 * np.float32(np.float32(1.0) - np.float32(0.045)))
+    rest = np.float32(lam32 - lam_t)
+    assert 0 < rest <= 0.09 * lam_t + 0.25
+    want = np.empty_like(got)
+    for s in range(n_s):
+        for w in range(n_b):
+            words = P.philox4x32_10([0x80000000, w, s >> 1, 1], key)
+            wu, wu2 = (words[2], words[3]) if (s & 1) else (words[0], words[1])
+            u = [np.float32(np.float64(np.float32(x)) * 2.0 ** -32 + 2.0 ** -33) for x in (wu, wu2)]
+            u = [min(float(x), 0.99999994) for x in u]
+            want[s, w] = stats.poisson.ppf(u[0], float(lam_t)) + stats.poisson.ppf(u[1], float(rest))
+    diff = got.astype(np.int64) - want
+    assert (diff != 0).mean() < 1e-3, (diff != 0).mean()
+    assert np.abs(diff).max() <= 1
