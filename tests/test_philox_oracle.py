@@ -109,3 +109,33 @@ def test_count_sampler_is_the_poisson_quantile_of_its_uniforms(lam):
     diff = got.astype(np.int64) - want
     assert (diff != 0).mean() < 1e-3, (diff != 0).mean()
     assert np.abs(diff).max() <= 1
+
+
+@pytest.mark.gpu
+def test_native_sky_draws_are_the_poisson_quantile_of_their_uniforms():
+    """k_reads_native's sky term, pixel by pixel and read by read: the count equals the exact
+    Poisson quantile of the uniform the oracle derives from the Philox call
+    (1, pixel pair, read, WB_STREAM_SKY) -- word x for the even pixel, y for the odd one."""
+    from scipy import stats
+    from tests.test_rng_gpu import _reads_noise_only
+    F, R, key, rate = 138, 3, (3, 4), 14.7
+    out = _reads_noise_only(sky_rate=rate, F=F, R=R, key=key, fast=1, dts=(1.0, 1.0, 1.0))
+    lam = float(np.float32(np.float32(1.0) * np.float32(rate * 1.0)))
+    B = 5
+    bad = n = 0
+    for r in range(R):
+        got = (out[r + 1] - out[r])[B:F - B, B:F - B]
+        assert np.all(got == np.rint(got))
+        for Y in range(B, F - B):
+            for X0 in range(B - (B & 1), F - B, 2):
+                words = P.philox4x32_10([1, Y * F + X0, r, 4], key)
+                for h in (0, 1):
+                    X = X0 + h
+                    if X < B or X >= F - B:
+                        continue
+                    u = float(np.float32((np.float64(words[h]) + 0.5) * 2.3283064365386963e-10))
+                    want = stats.poisson.ppf(min(u, 0.99999994), lam)
+                    n += 1
+                    bad += int(got[Y - B, X - B] != want)
+    assert n == R * (F - 2 * B) ** 2
+    assert bad < 1e-3 * n, (bad, n)
