@@ -139,3 +139,57 @@ def test_native_sky_draws_are_the_poisson_quantile_of_their_uniforms():
                     bad += int(got[Y - B, X - B] != want)
     assert n == R * (F - 2 * B) ** 2
     assert bad < 1e-3 * n, (bad, n)
+
+
+@pytest.mark.gpu
+def test_thrower_electrons_land_where_the_oracle_puts_them():
+    """The native thrower against an independent restatement of its whole recipe: Philox words
+    (oracle), 16-bit radius / angle fields, tail refinement from the second stream for radius
+    fields < 16, wide electrons first in units of four, Box-Muller in float64 with exact
+    functions.  Every electron must land in the oracle's pixel, except the few that fall
+    within float32 / SFU rounding (~1e-5 px) of a pixel edge."""
+    import math
+    from wayne_b200 import pyparallel
+    rng = np.random.default_rng(11)
+    nb, NR = 48, 128
+    counts = rng.integers(0, 4000, nb).astype(np.int32)
+    counts[5] = 0
+    counts[6] = 1
+    counts[7] = 5
+    x = 40.0 + rng.random(nb) * 48.0
+    y = 40.0 + rng.random(nb) * 48.0
+    ratio = rng.random(nb) * 0.6
+    sigl = 0.4 + rng.random(nb) * 0.5
+    sigh = 1.2 + rng.random(nb) * 1.0
+    test = 4321
+    got = pyparallel.psf_frame(counts, x, y, ratio, sigl, sigh, NR, NR, test=test, rng='philox')
+    assert got.sum() == counts.sum()                       # 8.2 sigma_h stays inside the frame
+    key = (test, 0x57415945)                               # wb200_psf_host's key pair
+    c32 = np.float32(2 * np.pi / 65536)
+    d32 = np.float32(-float(c32) * (2 ** 23 + 32768) + float(c32) / 2)
+    want = np.zeros((NR, NR), dtype=np.int64)
+    for w in range(nb):
+        cnt = int(counts[w])
+        nh = max(0, min(int(float(cnt) * ratio[w]), cnt))  # (int)(counts*ratio), pyparallel_menu.c:89
+        nl = cnt - nh
+        uh = (nh + 3) // 4
+        for j in range(uh + (nl + 3) // 4):
+            wide = j < uh
+            rem = (nh - 4 * j) if wide else (nl - 4 * (j - uh))
+            sigma = float(np.float32(sigh[w] if wide else sigl[w]))
+            words = P.thrower_words(j, 0, w, key)
+            tail = None
+            for h in range(min(4, rem)):
+                k, t = words[h] >> 16, words[h] & 0xffff
+                if k < 16:
+                    if tail is None:
+                        tail = P.thrower_words(j, 0, w, key, P.STREAM_PHOTON_TAIL)
+                    u1 = (k + (tail[h] + 0.5) / 2.0 ** 32) / 65536.0
+                else:
+                    u1 = (k + 0.5) / 65536.0
+                theta = float(np.float32(float(c32) * (2 ** 23 + t) + float(d32)))   # the device's fused form
+                r = math.sqrt(-2.0 * math.log(u1)) * sigma
+                px, py = x[w] + r * math.cos(theta), y[w] + r * math.sin(theta)
+                want[int(math.floor(py)), int(math.floor(px))] += 1
+    moved = np.abs(got.astype(np.int64) - want).sum() / 2
+    assert moved <= 5e-5 * counts.sum() + 3, (moved, counts.sum())
