@@ -2,6 +2,7 @@
 properties, since pylightcurve (the reference's third-party model) is not
 available here."""
 import numpy as np
+import pytest
 
 from wayne_b200 import lightcurve as lc
 
@@ -59,3 +60,37 @@ def test_chebyshev_signal_matches_direct_evaluation():
     assert np.abs(arr[:, ::37] - direct).max() < 1e-10
     assert np.allclose(sig[5], arr[5]) and np.allclose(sig[10:20].to_array(), arr[10:20])
     assert arr.max() > 0.015 and arr.min() == 0.0
+
+
+def test_linear_limb_darkening_centred_planet_closed_form():
+    # I = 1 - u (1 - mu): planet centred on the disk (z = 0), blocked light in closed form
+    for u_ld, p in ((0.6, 0.1), (0.3, 0.3), (1.0, 0.05)):
+        blocked = np.pi * p * p * (1 - u_ld) + 2 * np.pi * u_ld / 3 * (1 - (1 - p * p) ** 1.5)
+        total = np.pi * (1 - u_ld / 3)
+        f = lc.transit_flux(np.array([0.0]), np.array([p]), [0.0, u_ld, 0.0, 0.0])[0]
+        assert abs(f - (1 - blocked / total)) < 2e-10
+
+
+@pytest.mark.filterwarnings('ignore::scipy.integrate.IntegrationWarning')
+def test_against_two_dimensional_quadrature():
+    """An independent integrator: the limb-darkened intensity integrated over the planet's disk
+    in planet-centred Cartesian coordinates (scipy dblquad), for geometries inside the disk, on
+    the limb (ingress) and grazing."""
+    from scipy import integrate
+    c = LD
+
+    def inten(y, x, z):
+        r2 = (x + z) ** 2 + y * y
+        if r2 >= 1.0:
+            return 0.0
+        mu = np.sqrt(1 - r2)
+        sq = np.sqrt(mu)
+        return 1 - c[0] * (1 - sq) - c[1] * (1 - mu) - c[2] * (1 - mu * sq) - c[3] * (1 - mu * mu)
+
+    total = lc._claret_total(c)
+    for z, p in ((0.2, 0.12), (0.7, 0.1), (0.95, 0.1), (1.02, 0.12), (1.09, 0.1)):
+        blocked, _ = integrate.dblquad(inten, -p, p, lambda x: -np.sqrt(max(p * p - x * x, 0.0)),
+                                       lambda x: np.sqrt(max(p * p - x * x, 0.0)), args=(z,),
+                                       epsabs=1e-10, epsrel=1e-10)
+        f = lc.transit_flux(np.array([z]), np.array([p]), c)[0]
+        assert abs(f - (1 - blocked / total)) < 5e-6, (z, p, f, 1 - blocked / total)
