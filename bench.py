@@ -271,7 +271,9 @@ def run_reference(args, wk):
         return
     calibration_dir(wk)
     inp = make_inputs(wk)
-    n_sub = 8 * len(inp['read_index'])
+    # sub-samples per step: 8 per read interval for short runs, fewer when many steps are asked for, so
+    # that the whole --steps K --warmup W run stays within a few minutes (the line says what was sampled)
+    n_sub = max(2, min(8, 64 // max(1, args.steps))) * len(inp['read_index'])
     times, info = [], None
     for i in range(args.warmup + args.steps):
         t, info = cpu_reference_exposure(wk, inp, n_sub if i >= args.warmup else len(inp['read_index']),
