@@ -367,11 +367,14 @@ def run_native(args, wk):
     eng.profile = True               # stage events on in the warm-up too (first-use costs)
     phot_acc = torch.zeros((), dtype=torch.int64, device=dev)
     lost_acc = torch.zeros((1,), dtype=torch.int64, device=dev)
+    tally_acc = torch.zeros((2,), dtype=torch.int64, device=dev)
     n_warm = max(args.warmup, 8)     # long enough for the allocator pools to become stationary
     for i in range(n_warm):
         eg, _ = one(i, True)
         phot_acc += eg._run.d_totals.sum()           # same bookkeeping as the timed loop
         lost_acc += eg._run.lost
+        if eg._run.tally is not None:
+            tally_acc += eg._run.tally
         del eg
     barrier()
     from wayne_b200.engine import tune_host
@@ -385,6 +388,7 @@ def run_native(args, wk):
     st = torch.cuda.current_stream(dev)
     phot_acc.zero_()
     lost_acc.zero_()
+    tally_acc.zero_()
     torch.cuda.synchronize(dev)
     if os.environ.get('WB200_HOSTTRACE'):
         sys.stderr.write('[hosttrace] t=%.1f VALUE REGION START\n' % (time.perf_counter() * 1e3 % 1e6))
@@ -397,6 +401,8 @@ def run_native(args, wk):
         v_issue.append((time.perf_counter() - ta) * 1e3)
         phot_acc += eg._run.d_totals.sum()       # device-side bookkeeping, no sync
         lost_acc += eg._run.lost
+        if eg._run.tally is not None:
+            tally_acc += eg._run.tally           # [binned inside the frame, dropped outside it]
         geom = eg._run.win_geometry
         del eg
         if os.environ.get('WB200_HOSTTRACE') and (time.perf_counter() - ta) * 1e3 > 8:
@@ -414,6 +420,14 @@ def run_native(args, wk):
     photons = float(phot_acc.item()) / args.steps
     if int(lost_acc.item()):
         raise RuntimeError("electrons fell outside their sub-sample windows")
+    # electron conservation over the timed region, exact: every electron drawn was either
+    # binned into a read-interval plane or dropped outside the frame (pyparallel_menu.c:93)
+    binned, dropped = (int(v) for v in tally_acc.cpu().numpy())
+    thrown = int(phot_acc.item())
+    from wayne_b200 import params as _params
+    if _params.direct_accumulation and (binned + dropped != thrown or binned <= 0):
+        raise RuntimeError("electron bookkeeping of the timed exposures is off: %d binned + %d dropped != "
+                           "%d thrown" % (binned, dropped, thrown))
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside ---------------
     import collections
@@ -543,6 +557,8 @@ def run_native(args, wk):
         'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_value,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'photons_per_exposure': photons,
+        'electron_bookkeeping': {'thrown': thrown, 'binned_in_frame': binned, 'dropped_off_frame': dropped,
+                                 'check': 'binned + dropped == thrown over the timed exposures (asserted)'},
         'photons_per_s': world * photons * 1e3 / ms_value,
         'config': {'workload': wk['desc'], 'n_subsamples': N, 'n_bins': W, 'rng': 'philox',
                    'out_dtype': 'float64', 'window': [ww, wh], 'chunk_bins': chunk,

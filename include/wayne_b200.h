@@ -210,6 +210,11 @@ typedef struct wb200_photon_args {
     const int32_t *d_win_oy;
     uint64_t *d_lost;         /* [1] electrons inside the frame but outside their */
                               /* window (pre-zeroed; must stay 0)                 */
+    uint64_t *d_tally;        /* direct accumulation only, nullable, ADDED to:    */
+                              /* [0] electrons binned inside the frame, [1] the   */
+                              /* ones dropped outside it (pyparallel_menu.c:93),  */
+                              /* so [0] + [1] == sum(counts) of the sub-samples   */
+                              /* that belong to a read                            */
 } wb200_photon_args;
 
 int wb200_throw_photons(const wb200_photon_args *args, void *stream);

@@ -40,7 +40,7 @@ class PhotonArgs(C.Structure):
         ("d_wl", c_void_p), ("d_ratio", c_void_p), ("d_sigl", c_void_p), ("d_sigh", c_void_p),
         ("d_seeds", c_void_p), ("d_normals", c_void_p), ("d_normals_base", c_void_p),
         ("d_win", c_void_p), ("d_win_ox", c_void_p), ("d_win_oy", c_void_p),
-        ("d_lost", c_void_p),
+        ("d_lost", c_void_p), ("d_tally", c_void_p),
     ]
 
 

@@ -712,7 +712,12 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     // the sub-sample's flat-field / accumulation constants are CTA-uniform and only used by
     // the flush and by electrons that leave the tile: shared memory, not registers
     __shared__ DirectSample s_ds;
+    __shared__ unsigned long long s_tally[2]; // electrons binned inside the frame / dropped outside it
     DirectSample &ds = s_ds;
+    if (DIRECT && ga.d_read_end[ga.n_reads - 1] < (int)s_glob)
+        return; // a sub-sample after the last read belongs to no read (exposure_generator.py:361)
+    if (threadIdx.x == 0)
+        s_tally[0] = s_tally[1] = 0ull;
     if (DIRECT && threadIdx.x == 0) {
         const double *t = a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE;
         ds.g.ox = ds.g.oy = ds.g.s = ds.g.pad = 0;
@@ -881,11 +886,13 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                             continue;
                         const int xa = ix[e] + ax0, ya = iy[e] + ay0;
                         if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
-                            if (DIRECT)
+                            if (DIRECT) {
                                 deposit(ga, ds, xa, ya, 1);
-                            else
+                                atomicAdd(&s_tally[0], 1ull);
+                            } else
                                 to_window(a, s_local, wox, woy, xa, ya);
-                        }
+                        } else if (DIRECT)
+                            atomicAdd(&s_tally[1], 1ull); // dropped like the reference's (pyparallel_menu.c:93)
                     }
                 }
             }
@@ -895,12 +902,14 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     __syncthreads();
 
     // ---- flush the tile ---------------------------------------------------------
+    unsigned binned = 0;
     for (int i = threadIdx.x; i < TW * TH; i += blockDim.x) {
         const int v = tile[i];
         if (v) {
             const int iy = i / TW, ix = i - iy * TW;
             if (DIRECT) {
                 deposit(ga, ds, ix + tx0, iy + ty0, v);
+                binned += (unsigned)v;
             } else {
                 const int wx = ix + tx0 - wox, wy = iy + ty0 - woy;
                 if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
@@ -909,6 +918,15 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                     atomicAdd((unsigned long long *)a.d_lost, (unsigned long long)v);
             }
         }
+    }
+    if (DIRECT && a.d_tally) {
+        // electron bookkeeping of the exposure: binned + dropped == thrown, exactly
+        binned = __reduce_add_sync(FULL, binned);
+        if (lane == 0 && binned)
+            atomicAdd(&s_tally[0], (unsigned long long)binned);
+        __syncthreads();
+        if (threadIdx.x < 2 && s_tally[threadIdx.x])
+            atomicAdd((unsigned long long *)a.d_tally + threadIdx.x, s_tally[threadIdx.x]);
     }
 }
 

@@ -445,6 +445,7 @@ class ExposureRun(object):
         self.d_expected = None
         self.d_acc = None
         self.lost = e.zeros((1,), torch.int64)
+        self.tally = None                  # direct path: [binned in frame, dropped outside it]
 
     def _release_depth(self):
         """The planet-signal upload buffer may be overwritten by a later exposure
@@ -642,6 +643,8 @@ class ExposureRun(object):
         ga.n_samples, ga.sample0 = N, 0
         ga.d_trace = self.d_trace.data_ptr()
         ga.d_acc = self.d_acc.data_ptr()
+        self.tally = e.zeros((2,), torch.int64)
+        pa.d_tally = self.tally.data_ptr()
         e.mark('k_throw', True)
         check(lib.wb200_throw_photons_direct(C.byref(pa), C.byref(ga), 0, e.stream_ptr()),
               "wb200_throw_photons_direct")
