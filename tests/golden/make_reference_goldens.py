@@ -190,6 +190,22 @@ out['ssv_dur'] = dur
 out['ssv_out'] = ssv['SSVSine'](1.5, 1.1, 0).get_subsample_exposure_times(ymid, dur, None, None)
 out['ssv_out_phase'] = ssv['SSVSine'](2.5, 0.7, 1.3).get_subsample_exposure_times(ymid, dur, None, None)
 
+# SSVModulatedSine (scan_speed_varations.py:63-171): stochastic; numpy's global RandomState seeded,
+# so the golden also pins the ORDER in which the body consumes it
+ssvm = extract('trend_generators/scan_speed_varations.py', ['SSVModulatedSine'])
+for tag, seed, amp, per, blip, rt, rate in (
+        ('a', 1963, 10, 1.1, 1, [0.278, 7.624, 14.971, 22.317], 0.05),
+        ('blip', 7, 5, 0.8, 100, [2.932 * k for k in range(1, 6)], 0.02),
+        ('c', 20170410, 10, 1.1, 0, [0.278, 7.624, 14.971, 22.317], 0.1)):
+    np.random.seed(seed)
+    d_, ri_ = ssvm['SSVModulatedSine'](amp, per, blip).get_subsample_exposure_times(
+        None, None, np.array(rt) * U.s, rate * U.s)
+    out['ssvm_%s_args' % tag] = np.array([seed, amp, per, blip, rate], dtype=float)
+    out['ssvm_%s_rt' % tag] = np.array(rt)
+    out['ssvm_%s_dur_ms' % tag] = np.asarray(U.value_in(d_, U.ms), dtype=float)
+    out['ssvm_%s_ri' % tag] = np.array(ri_)
+    out['ssvm_%s_next_random' % tag] = np.float64(np.random.random())     # stream position afterwards
+
 vt = extract('trend_generators/visit_trends.py', ['BaseVisitTrend', 'HookAndLongTermRamp',
                                                   'gen_orbit_start_times_per_exp'], ns={'abc': __import__('abc')})
 t = np.sort(rng.uniform(2456196.1, 2456196.5, 40))
@@ -214,6 +230,34 @@ for tag, rt, rate in (('c1', [0.278, 7.624, 14.971, 22.317], 10.0),
     out['times_%s_rt' % tag] = np.array(rt)
     yrefs = eg['ExposureGenerator']._gen_sample_yref(me, 457.4, mids, (7.4325 * U.pixel / U.s).to(U.pixel / U.ms))
     out['times_%s_yref' % tag] = np.asarray(yrefs, dtype=float)
+
+# ---- exposure_generator.py: direct_image (:83-144) ----------------------------------------------
+class _RecExposure(object):
+    def __init__(self, det_, filt, planet, exp_info):
+        self.filt, self.exp_info, self.reads = filt, dict(exp_info), []
+
+    def add_read(self, data, read_info=None):
+        self.reads.append((np.array(data, dtype=float), read_info))
+
+
+eg['exposure'] = types.SimpleNamespace(Exposure=_RecExposure)
+eg['filters'] = types.SimpleNamespace(F140W=lambda: types.SimpleNamespace(name='F140W'))
+eg['ExposureGenerator'].direct_image.__globals__.update(exposure=eg['exposure'], filters=eg['filters'])
+for tag, sub, xr_, yr_ in (('256', 256, 404.497, 457.427), ('512', 512, 390.25, 610.75), ('64', 64, 506.1, 498.3)):
+    me = types.SimpleNamespace(
+        exp_info={}, planet=None, SUBARRAY=sub,
+        detector=types.SimpleNamespace(gen_pixel_array=lambda s_, light_sensitive=True, _d=d['WFC3_IR']:
+                                       _d.gen_pixel_array(None, s_, light_sensitive)))
+    ex = eg['ExposureGenerator'].direct_image(me, xr_, yr_)
+    assert len(ex.reads) == 2 and ex.filt.name == 'F140W'
+    out['direct_%s_args' % tag] = np.array([sub, xr_, yr_])
+    out['direct_%s_zero_shape' % tag] = np.array(ex.reads[0][0].shape)
+    out['direct_%s_zero_sum' % tag] = np.float64(np.abs(ex.reads[0][0]).sum())
+    out['direct_%s_image' % tag] = ex.reads[1][0]
+    out['direct_%s_crpix1' % tag] = np.int64(ex.reads[1][1]['CRPIX1'])
+    out['direct_%s_info' % tag] = np.array([me.exp_info['NSAMP'], me.exp_info['cosmic_rate'],
+                                            me.exp_info['scale_factor']], dtype=float)
+    out['direct_%s_obstype' % tag] = np.array(me.exp_info['OBSTYPE'] + '|' + me.exp_info['SAMP-SEQ'])
 
 np.savez_compressed(os.path.join(HERE, 'reference_goldens.npz'), **out)
 print('wrote', len(out), 'arrays;', os.path.getsize(os.path.join(HERE, 'reference_goldens.npz')), 'bytes')

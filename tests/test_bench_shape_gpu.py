@@ -142,7 +142,7 @@ def test_c4_native_pixels_match_analytic_expectation(calb_dir):
     for r in range(14):
         assert abs(got[r].sum() - exp[r].sum()) < 6 * np.sqrt(exp[r].sum()), r
     m = exp > 50
-    assert m.sum() > 2e5
+    assert m.sum() > 1.5e5
     z = (got[m] - exp[m]) / np.sqrt(exp[m])
     assert abs(z.mean()) < 6 / np.sqrt(m.sum())
     assert 0.95 < z.std() < 1.03

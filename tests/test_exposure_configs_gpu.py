@@ -178,3 +178,57 @@ def test_direct_path_full_frame_matches_gather_path(calb_dir, monkeypatch):
     assert b.max() > 10 and np.abs(a - b).max() / b.max() < 1e-7
     # the source sits in the corner: light reaches the first rows/columns of the light-sensitive area
     assert b[-1][5:40, 5:200].sum() > 0
+
+
+def test_ssv_modulated_sine_exposure(calb_dir):
+    """SSVModulatedSine (scan_speed_varations.py:63-171) through the exposure path: it replaces
+    the durations AND the read indexes (exposure_generator.py:262-273) and comes out one
+    sub-sample short, so the last sub-sample has zero duration (:340-342) and sub-samples after
+    the last read index never reach a read (:361).  Compat mode: the generator draws from the
+    numpy stream BEFORE the per-sub-sample seeds (A.7), which the oracle side replays."""
+    from wayne import detector, grism
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator
+    from wayne.trend_generators.scan_speed_varations import SSVModulatedSine
+    from wayne_b200 import calibration
+    calibration.write_synthetic_calibration(calb_dir, modes=((256, 'SPARS10'),))
+    cal = harness.oracle_calibration('G141', dark_mode=(256, 'SPARS10'), nsamp=5)
+    wl, flux, planet = harness.spectrum(level=4.0e-14)
+    eg = ExposureGenerator(detector.WFC3_IR(), grism.G141(), 5, 'SPARS10', 256, None, rng='numpy')
+    rate = 50.0
+    np.random.seed(77)
+    exp = eg.scanning_frame(404.5, 457.4, 0.02, 0.02, wl * u.micron, flux, None, 7.4325 * u.pixel / u.s,
+                            rate * u.ms, ssv_generator=SSVModulatedSine(10, 1.1, 100), cosmic_rate=11.,
+                            sky_background=2.0 * u.count / u.s, threads=2)
+    # oracle side: the same generator call on the same stream, then the oracle's own loop
+    rt = eg.read_times.to(u.s).value
+    _, mid, dur0, _ = E.gen_scanning_sample_times(rt, rate)
+    np.random.seed(77)
+    dur, ri = SSVModulatedSine(10, 1.1, 100).get_subsample_exposure_times(None, None, eg.read_times, rate * u.ms)
+    dur = np.asarray(u.value_in(dur, u.ms))
+    assert len(dur) < len(mid) and ri != list(E.gen_scanning_sample_times(rt, rate)[3])
+    dur = np.concatenate([dur, np.zeros(len(mid) - len(dur))])
+    rs = np.random.RandomState()
+    rs.set_state(np.random.get_state())
+    o = E.scanning_frame(cal, 'G141', 256, rt, wl, flux, None, 404.5, 457.4, 0.02, 0.02, 7.4325 * 0.001, rate,
+                         rs, cosmic_rate=11., sky_background=2.0, threads=2,
+                         sample_times=(mid, dur, [int(i) for i in ri]))
+    assert o['photons'] > 1e6
+    _check(exp, o, eg)
+    # native mode: the same generator object works there too, and both accumulation paths drop
+    # the sub-samples after the last read index
+    out = {}
+    from wayne_b200 import params
+    for direct in (True, False):
+        params.direct_accumulation = direct
+        try:
+            np.random.seed(78)
+            eg2 = ExposureGenerator(detector.WFC3_IR(), grism.G141(), 5, 'SPARS10', 256, None, rng='philox')
+            e2 = eg2.scanning_frame(404.5, 457.4, 0.02, 0.02, wl * u.micron, flux, None, 7.4325 * u.pixel / u.s,
+                                    rate * u.ms, ssv_generator=SSVModulatedSine(10, 1.1, 100), cosmic_rate=None,
+                                    sky_background=0 * u.count / u.s, add_dark=False, add_non_linear=False,
+                                    add_read_noise=False, rng_key=(3, 4))
+            out[direct] = np.array([r[0] for r in e2.reads])
+        finally:
+            params.direct_accumulation = True
+    assert out[False].max() > 10 and np.abs(out[True] - out[False]).max() / out[False].max() < 1e-7

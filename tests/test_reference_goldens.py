@@ -143,3 +143,43 @@ def test_sample_timing(tag, nsamp, seq, sub, rate):
         npt.assert_allclose(u.value_in(m, u.ms), G['times_%s_mid' % tag], rtol=1e-14)
         npt.assert_allclose(u.value_in(d, u.ms), G['times_%s_dur' % tag], rtol=1e-12, atol=1e-9)
         assert list(r) == list(G['times_%s_ri' % tag])
+
+
+@pytest.mark.parametrize("tag", ['a', 'blip', 'c'])
+def test_ssv_modulated_sine(tag):
+    """SSVModulatedSine.get_subsample_exposure_times (scan_speed_varations.py:83-171) against the
+    executed reference body: same numpy RandomState seed -> the same sub-sample durations to the
+    last bit, the same read indexes, and the stream left at the same position (i.e. the mirror
+    consumes numpy's global state draw for draw, blips and the 1 us redistribution included)."""
+    seed, amp, per, blip, rate = G['ssvm_%s_args' % tag]
+    rt = G['ssvm_%s_rt' % tag]
+    np.random.seed(int(seed))
+    gen = scan_speed_varations.SSVModulatedSine(amp, per, blip)
+    dur, ri = gen.get_subsample_exposure_times(None, None, rt * u.s, rate * u.s)
+    assert np.array_equal(np.asarray(u.value_in(dur, u.ms)), G['ssvm_%s_dur_ms' % tag])
+    assert [int(i) for i in ri] == [int(i) for i in G['ssvm_%s_ri' % tag]]
+    assert np.random.random() == float(G['ssvm_%s_next_random' % tag])
+    # what the body promises: the exposure time is kept to the microsecond
+    assert abs(np.sum(G['ssvm_%s_dur_ms' % tag]) * 1e-3 - rt[-1]) < 2e-6
+
+
+@pytest.mark.parametrize("tag", ['256', '512', '64'])
+def test_direct_image_values(tag):
+    """ExposureGenerator.direct_image (exposure_generator.py:83-144) against the executed
+    reference body: zero read F x F of zeros, second read the S x S Gaussian (B11: no border),
+    CRPIX1 -5, exp_info switches."""
+    sub, xr, yr = G['direct_%s_args' % tag]
+    sub = int(sub)
+    seq = {256: 'SPARS10', 512: 'SPARS25', 64: 'RAPID'}[sub]
+    eg = ExposureGenerator(detector.WFC3_IR(), grism.G141(), 3, seq, sub, None)
+    ex = eg.direct_image(float(xr), float(yr))
+    assert len(ex.reads) == 2
+    zero, img = ex.reads[0][0], ex.reads[1][0]
+    assert tuple(zero.shape) == tuple(G['direct_%s_zero_shape' % tag]) and np.abs(zero).sum() == 0.0
+    assert float(G['direct_%s_zero_sum' % tag]) == 0.0
+    assert np.array_equal(img, G['direct_%s_image' % tag])
+    assert img.shape == (sub, sub) and img.max() > 5000
+    assert ex.reads[1][1]['CRPIX1'] == int(G['direct_%s_crpix1' % tag]) == -5
+    info = eg.exp_info
+    assert [info['NSAMP'], info['cosmic_rate'], info['scale_factor']] == list(G['direct_%s_info' % tag])
+    assert info['OBSTYPE'] + '|' + info['SAMP-SEQ'] == str(G['direct_%s_obstype' % tag])
