@@ -94,3 +94,40 @@ def test_against_two_dimensional_quadrature():
                                        epsabs=1e-10, epsrel=1e-10)
         f = lc.transit_flux(np.array([z]), np.array([p]), c)[0]
         assert abs(f - (1 - blocked / total)) < 5e-6, (z, p, f, 1 - blocked / total)
+
+
+def test_planet_signal_carries_the_secondary_eclipse_term():
+    """The reference feeds the frames planet_depths = 1 - (transit - (1 - eclipse))
+    (wayne/observation.py:338-343, 441-443): during secondary eclipse the star is dimmed by
+    (1 - eclipse(fp = depth[w], rp_body)) too.  The Chebyshev form the device path uses must
+    equal the dense evaluation at every phase: transit, eclipse ingress / totality, and out
+    of both."""
+    from wayne import observation
+    from wayne import units as u
+    obs = observation.Observation()
+    star = observation.Star(R=1.155)
+    planet = observation.Planet(name='HD 209458 b', P=HD['period'], a=0.047309, R=1.38, i=HD['inc_deg'],
+                                e=0.0, periastron=0.0, transittime=HD['t0'], star=star)
+    wl = np.linspace(1.0, 1.7, 211)
+    depth = 0.0146 * (1 + 0.02 * np.sin(9 * wl))
+    obs.setup_target(planet, wl * u.micron, depth, np.ones_like(wl), ldcoeffs=LD)
+    rp_body = obs._rp_body()
+    assert abs(rp_body - 1.38 * 0.10045 / 1.155) < 1e-12
+    mid_ecl = HD['t0'] + HD['period'] / 2
+    # (at the transit's contact points the signal has a kink in rp: the order-8 expansion is good
+    # to 5e-8 there, 3e-6 of the depth; the eclipse term is a smooth function of rp and exact)
+    for t, tol in ((HD['t0'] + np.linspace(-0.08, 0.08, 41), 1e-7),            # transit
+                   (mid_ecl + np.linspace(-0.085, -0.03, 37), 1e-12),          # eclipse ingress into totality
+                   (mid_ecl + np.linspace(-0.01, 0.01, 9), 1e-12),             # totality
+                   (HD['t0'] + 0.9 + np.linspace(0, 0.02, 5), 1e-15)):         # neither
+        dense = 1 - obs.generate_lightcurves(t * u.day)
+        cheb = obs._planet_signal(t * u.day, device=False).to_array()
+        assert dense.shape == cheb.shape == (len(t), len(wl))
+        assert np.abs(dense - cheb).max() < tol
+        if tol == 1e-12:
+            assert dense.max() > 0.01                                          # the term is really there
+    tot = 1 - obs.generate_lightcurves(np.array([mid_ecl]) * u.day)[0]
+    assert np.allclose(tot, depth / (1 + depth), rtol=1e-12)             # planet fully hidden
+    # without a planet radius there is no eclipse term (as when rp is not configured)
+    planet.R = None
+    assert np.all(obs._planet_signal(np.array([mid_ecl]) * u.day, device=False).to_array() == 0)

@@ -135,3 +135,28 @@ def test_device_transit_kernel_matches_host_model():
     t = orb['t0'] + np.linspace(-0.1, 0.1, 101)
     assert np.abs(lc.planet_signal_device(DeviceEngine.get(), t, depth, LD, **e).to_array()
                   - lc.planet_signal(t, depth, LD, **e).to_array()).max() < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ssv_type,coeffs", [('mod-sine', [10, 1.1, 100]), ('sine', [1.5, 1.1, 'rand'])])
+def test_sharded_visit_with_stochastic_ssv_is_partition_independent(tmp_path, calb_dir, ssv_type, coeffs):
+    """Scan-speed-variation generators draw from numpy's global stream (scan_speed_varations.py:45,
+    100-132).  With the visit spread over ranks each rank has drawn a different number of values
+    before a given exposure; the frames must not depend on that."""
+    pfile = _write_visit(tmp_path, n_exp=4)
+    with open(pfile) as fh:
+        cfg = yaml.safe_load(fh)
+    cfg['observation']['ssv_type'] = ssv_type
+    cfg['observation']['ssv_coeffs'] = coeffs
+    frames = {}
+    for tag, shards in (('one', [(0, 1)]), ('two', [(0, 2), (1, 2)])):
+        cfg['general']['outdir'] = 'out_' + tag
+        got = {}
+        for shard in shards:
+            obs = run_visit.build_observation(cfg, str(tmp_path))       # reseeds numpy like a fresh rank
+            got.update(obs.run_observation(shard=shard, write_fits=False))
+        frames[tag] = {n: np.array([r[0] for r in e.reads]) for n, e in got.items()}
+    assert sorted(frames['one']) == sorted(frames['two']) == [1, 2, 3, 4]
+    for n in (1, 2, 3, 4):
+        assert np.array_equal(frames['one'][n], frames['two'][n]), n
+    assert not np.array_equal(frames['one'][1][-1], frames['one'][2][-1])

@@ -249,13 +249,27 @@ class ExposureGenerator(object):
         mid_ms = _ms(sample_mid_points)
         s_y_refs = y_ref + mid_ms * scan_speed_ms
 
+        key = tuple(int(k) for k in (rng_key if rng_key is not None else self._default_key(compat)))
         if ssv_generator is not None:
-            if isinstance(ssv_generator, scan_speed_varations.SSVModulatedSine):
-                sample_durations, read_index = ssv_generator.get_subsample_exposure_times(
-                    s_y_refs, sample_durations, self.read_times, sample_rate_q)
-            else:
-                sample_durations = ssv_generator.get_subsample_exposure_times(
-                    s_y_refs, sample_durations, self.read_times, sample_rate_q)
+            # the generators draw from numpy's global stream (scan_speed_varations.py:45, 100-132).
+            # compat: that IS the reference's stream and its order (A.7).  native: the draws of an
+            # exposure must depend on its key only -- not on how many exposures this process has
+            # generated before, i.e. not on how a visit is spread over GPUs -- so the global
+            # stream is keyed for the call and put back afterwards.
+            saved = None
+            if not compat:
+                saved = np.random.get_state()
+                np.random.seed([key[0], key[1], 0x55F])
+            try:
+                if isinstance(ssv_generator, scan_speed_varations.SSVModulatedSine):
+                    sample_durations, read_index = ssv_generator.get_subsample_exposure_times(
+                        s_y_refs, sample_durations, self.read_times, sample_rate_q)
+                else:
+                    sample_durations = ssv_generator.get_subsample_exposure_times(
+                        s_y_refs, sample_durations, self.read_times, sample_rate_q)
+            finally:
+                if saved is not None:
+                    np.random.set_state(saved)
         dur_ms = _ms(sample_durations)
 
         self.exp_info.update({
@@ -288,7 +302,6 @@ class ExposureGenerator(object):
         if len(dur_ms) < num_samples:      # bad SSV output: missing durations count as 0 (:340-342)
             dur_ms = np.concatenate([dur_ms, np.zeros(num_samples - len(dur_ms))])
         dt_s = np.diff(np.concatenate([[0.0], read_times_s]))
-        key = tuple(int(k) for k in (rng_key if rng_key is not None else self._default_key(compat)))
 
         eng = DeviceEngine.get(self.device)
         eng.admit()

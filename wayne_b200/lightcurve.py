@@ -116,8 +116,8 @@ def transit(ldcoeffs, rp, period, a, e, inc_deg, w_deg, t0, t, nodes=96):
     return transit_flux(z, np.full(z.shape, float(rp)), ldcoeffs, nodes)
 
 
-def eclipse(fp_over_fs, rp, period, a, e, inc_deg, w_deg, t0, t):
-    """Secondary eclipse of a uniformly bright planet: (1 + fp * visible) / (1 + fp)."""
+def eclipse_visibility(rp, period, a, e, inc_deg, w_deg, t0, t):
+    """Fraction of the planet's disk (radius ratio rp) NOT hidden behind the star at times t."""
     z, front = kepler_separation(t, period, a, e, inc_deg, w_deg, t0)
     z = np.where(front, np.inf, z)
     p = float(rp)
@@ -131,14 +131,54 @@ def eclipse(fp_over_fs, rp, period, a, e, inc_deg, w_deg, t0, t):
         k1 = np.arccos(np.clip((1 - p * p + zz * zz) / (2 * zz), -1, 1))
         area = p * p * k0 + k1 - 0.5 * np.sqrt(np.clip(4 * zz * zz - (1 + zz * zz - p * p) ** 2, 0, None))
         vis[part] = 1 - area / (np.pi * p * p)
+    return vis
+
+
+def eclipse(fp_over_fs, rp, period, a, e, inc_deg, w_deg, t0, t):
+    """Secondary eclipse of a uniformly bright planet: (1 + fp * visible) / (1 + fp)."""
+    vis = eclipse_visibility(rp, period, a, e, inc_deg, w_deg, t0, t)
     return (1 + fp_over_fs * vis) / (1 + fp_over_fs)
 
 
+def _cheb_nodes(order, pmin, pmax):
+    k = np.arange(order)
+    xk = np.cos(np.pi * (k + 0.5) / order)
+    return k, 0.5 * (pmax - pmin) * xk + 0.5 * (pmax + pmin)
+
+
+def _cheb_transform(f, order):
+    """Chebyshev coefficients [..., order] of node values f [..., order]."""
+    k = np.arange(order)
+    T = np.cos(np.pi * np.outer(k, k + 0.5) / order)                       # T_j(x_k)
+    coef = (2.0 / order) * f @ T.T
+    coef[..., 0] *= 0.5
+    return coef
+
+
+def eclipse_cheb_term(t, rp_body, order, pmin, pmax, period, a, e, inc_deg, w_deg, t0):
+    """The secondary-eclipse part of the reference's planet signal as Chebyshev
+    coefficients [n_samples][order], or None when no sample is in eclipse.
+
+    The reference dims the star by 1 - eclipse(fp = depth[w], rp_body, t) as well
+    (wayne/observation.py:338-343, 441-443: planet_depths = 1 - (transit - (1 -
+    eclipse))).  With a uniformly bright planet that is
+        (1 - visible(t)) * fp / (1 + fp),   fp = rp[w]^2,
+    a product of a per-sample factor and a smooth function of the bin's radius
+    ratio -- the same expansion variable as the transit term."""
+    hidden = 1.0 - eclipse_visibility(rp_body, period, a, e, inc_deg, w_deg, t0, t)
+    if not np.any(hidden > 0):
+        return None
+    _, pk = _cheb_nodes(order, pmin, pmax)
+    g = _cheb_transform((pk * pk / (1 + pk * pk))[None, :], order)[0]
+    return hidden[:, None] * g[None, :]
+
+
 def planet_signal_device(engine, t, depth_spectrum, ldcoeffs, period, a, e, inc_deg, w_deg, t0, order=8,
-                         nodes=96):
+                         nodes=96, rp_body=None):
     """:func:`planet_signal` with the quadrature on the GPU (wb200_transit_cheb):
     the coefficients stay in HBM and go straight into k_counts.  The host only
-    solves Kepler's equation for the sub-sample times."""
+    solves Kepler's equation for the sub-sample times (and adds the secondary-
+    eclipse term on the rare exposures that see one)."""
     import ctypes as C
 
     from . import _lib
@@ -157,6 +197,11 @@ def planet_signal_device(engine, t, depth_spectrum, ldcoeffs, period, a, e, inc_
                                            ld.ctypes.data_as(_lib.DP), nodes, C.c_void_p(glx.data_ptr()),
                                            C.c_void_p(glw.data_ptr()), C.c_void_p(coef.data_ptr()),
                                            engine.stream_ptr()), "wb200_transit_cheb")
+    if rp_body:
+        ecl = eclipse_cheb_term(t, rp_body, order, pmin, pmax, period, a, e, inc_deg, w_deg, t0)
+        if ecl is not None:
+            d_ecl, = engine.to_dev_many([ecl], ahead=True)
+            coef += d_ecl
     x = (2 * rp - (pmax + pmin)) / (pmax - pmin)
     return ChebyshevSignal(coef, x)
 
@@ -188,23 +233,26 @@ class ChebyshevSignal(object):
         return np.polynomial.chebyshev.chebval(self.x, self._host_coef().T)
 
 
-def planet_signal(t, depth_spectrum, ldcoeffs, period, a, e, inc_deg, w_deg, t0, order=8, nodes=96):
-    """ChebyshevSignal of 1 - transit(t; rp = sqrt(depth[w])) for sample times t
-    [days] and a transit-depth spectrum (what Observation.generate_lightcurves
-    returns as ``1 - star_norm_flux``, wayne/observation.py:441-443)."""
+def planet_signal(t, depth_spectrum, ldcoeffs, period, a, e, inc_deg, w_deg, t0, order=8, nodes=96,
+                  rp_body=None):
+    """ChebyshevSignal of the reference's planet signal for sample times t [days]
+    and a transit-depth spectrum: ``1 - star_norm_flux`` of wayne/observation.py:
+    441-443 with star_norm_flux = transit(rp = sqrt(depth[w])) - (1 - eclipse(fp =
+    depth[w], rp_body)) (:338-343).  ``rp_body`` = the planet's radius ratio used
+    for the secondary eclipse (None: no eclipse term, as when the planet has no
+    radius)."""
     rp = np.sqrt(np.asarray(depth_spectrum, dtype=np.float64))
     pmin, pmax = float(rp.min()), float(rp.max())
     if pmax - pmin < 1e-12:
         pmax = pmin + 1e-12
-    k = np.arange(order)
-    xk = np.cos(np.pi * (k + 0.5) / order)                     # Chebyshev nodes
-    pk = 0.5 * (pmax - pmin) * xk + 0.5 * (pmax + pmin)
+    _, pk = _cheb_nodes(order, pmin, pmax)
     z, front = kepler_separation(t, period, a, e, inc_deg, w_deg, t0)
     z = np.where(front, z, np.inf)
     f = 1 - transit_flux(z[:, None], pk[None, :], ldcoeffs, nodes)        # [N][order]
-    # discrete Chebyshev transform
-    T = np.cos(np.pi * np.outer(k, k + 0.5) / order)                       # T_j(x_k)
-    coef = (2.0 / order) * f @ T.T
-    coef[:, 0] *= 0.5
+    coef = _cheb_transform(f, order)
+    if rp_body:
+        ecl = eclipse_cheb_term(t, rp_body, order, pmin, pmax, period, a, e, inc_deg, w_deg, t0)
+        if ecl is not None:
+            coef = coef + ecl
     x = (2 * rp - (pmax + pmin)) / (pmax - pmin)
     return ChebyshevSignal(coef, x)

@@ -168,6 +168,11 @@ class Observation(object):
         return dict(period=float(p.P), a=a_rs, e=float(p.e or 0.0), inc_deg=float(p.i), w_deg=w,
                     t0=float(p.transittime))
 
+    def _rp_body(self):
+        """Planet radius / stellar radius used by the secondary-eclipse term (None: no term)."""
+        p = self.planet
+        return float(p.R) * RJUP_IN_RSUN / float(p.star.R) if (p.R and p.star.R) else None
+
     def generate_lightcurves(self, time_array, depth=False):
         """[len(time_array)][len(spectrum)] relative flux: transit - (1 - eclipse),
         as observation.py:293-357 (dense host evaluation; the exposure path uses
@@ -175,7 +180,7 @@ class Observation(object):
         t = np.asarray(u.value_in(time_array, u.day), dtype=float)
         spectrum = np.array([depth]) if depth else np.asarray(self.planet_spectrum, dtype=float)
         orb = self._orbit()
-        rp_body = float(self.planet.R) * RJUP_IN_RSUN / float(self.planet.star.R) if self.planet.R else None
+        rp_body = self._rp_body()
         models = np.zeros((len(t), len(spectrum)))
         for j, d in enumerate(spectrum):
             m = lightcurve.transit(self.ldcoeffs, np.sqrt(d), t=t, **orb)
@@ -185,16 +190,20 @@ class Observation(object):
         return models
 
     def _planet_signal(self, time_array, device=True):
-        """Chebyshev planet signal of one exposure's sub-sample times; with a CUDA
-        device the quadrature runs on the GPU (wb200_transit_cheb)."""
+        """Chebyshev planet signal of one exposure's sub-sample times, equal to
+        ``1 - generate_lightcurves(time_array)`` (transit AND secondary-eclipse terms,
+        observation.py:338-343, 441-443); with a CUDA device the transit quadrature
+        runs on the GPU (wb200_transit_cheb)."""
         t = np.asarray(u.value_in(time_array, u.day), dtype=float)
         if device:
             import torch
             if torch.cuda.is_available():
                 from .engine import DeviceEngine
                 return lightcurve.planet_signal_device(DeviceEngine.get(), t, self.planet_spectrum,
-                                                       self.ldcoeffs, **self._orbit())
-        return lightcurve.planet_signal(t, self.planet_spectrum, self.ldcoeffs, **self._orbit())
+                                                       self.ldcoeffs, rp_body=self._rp_body(),
+                                                       **self._orbit())
+        return lightcurve.planet_signal(t, self.planet_spectrum, self.ldcoeffs, rp_body=self._rp_body(),
+                                        **self._orbit())
 
     # -- the visit ------------------------------------------------------------
     def run_observation(self, shard=None, pipeline_depth=3, write_fits=True):
@@ -202,6 +211,12 @@ class Observation(object):
         rank's exposure-wise share).  Returns {file number: path or Exposure}."""
         results = {}
         rank, world = shard if shard is not None else (0, 1)
+        from . import params
+        if world > 1 and (self.rng or params.rng) == 'numpy':
+            # the compat mode consumes ONE sequential numpy stream across the exposures of a visit
+            # (run_visit.py:73-77): ranks seeded alike would repeat each other's noise realisations
+            raise ValueError("rng='numpy' (the reference's sequential streams) cannot be sharded over "
+                             "{} ranks; use rng='philox'".format(world))
         if rank == 0:
             self._generate_direct_image()
         numbers = [i + 1 for i in sharding.shard_indices(len(self.exp_start_times), world, rank)]

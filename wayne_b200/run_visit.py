@@ -1,5 +1,5 @@
 """Usage:
-    wayne -p <parameter_file> [--gpus <n>]
+    wayne -p <parameter_file> [--gpus <n>] [--max-exposures <k>]
 
 Runs a visit from a YAML parameter file -- the ``wayne`` command of the
 reference (wayne/run_visit.py:1-324, setup.py:56-60) with the same file format
@@ -10,7 +10,10 @@ spectrum file is given; the reference reads it from the Open Exoplanet
 Catalogue, which is not available), ``general.rng`` ('philox' | 'numpy').
 
 Exposures are generated on the GPU(s) by wayne_b200.observation.Observation;
-with ``--gpus n`` (or under torchrun) the visit is partitioned exposure-wise.
+with ``--gpus n`` (one child process per GPU, spawned here) or under torchrun the
+visit is partitioned exposure-wise.  A visit without ``general.seed`` gets ONE
+seed for all ranks (drawn by the parent / by rank 0), so the frames and the
+RANDSEED headers do not depend on the GPU count.
 """
 from __future__ import annotations
 
@@ -39,6 +42,30 @@ def _get(cfg, section, key, default=None):
     return v
 
 
+def shared_visit_seed(seed=None):
+    """The visit's seed, identical on every rank: the parameter file's, else the one
+    the ``--gpus`` parent handed down (WAYNE_B200_VISIT_SEED), else drawn by rank 0 and
+    broadcast (a two-line gloo exchange under torchrun; the data path has no collective)."""
+    if seed:
+        return int(seed)
+    env = os.environ.get('WAYNE_B200_VISIT_SEED')
+    if env:
+        return int(env)
+    s = int.from_bytes(os.urandom(4), 'little') & 0x7fffffff
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1 and os.environ.get('MASTER_ADDR'):
+        import torch
+        import torch.distributed as dist
+        made = not dist.is_initialized()
+        if made:
+            dist.init_process_group('gloo')
+        t = torch.tensor([s], dtype=torch.int64)
+        dist.broadcast(t, 0)
+        s = int(t.item())
+        if made:
+            dist.destroy_process_group()
+    return s
+
+
 def build_observation(cfg, base_dir='.'):
     """Wire an Observation from a parsed parameter file (run_visit.py:47-314)."""
     def path(p):
@@ -46,9 +73,9 @@ def build_observation(cfg, base_dir='.'):
 
     outdir = path(cfg['general']['outdir'])
     os.makedirs(outdir, exist_ok=True)
-    seed = _get(cfg, 'general', 'seed')
-    np.random.seed(seed if seed else None)
-    params.seed = int(seed) if seed else int(np.random.get_state()[1][0])
+    seed = shared_visit_seed(_get(cfg, 'general', 'seed'))
+    np.random.seed(seed)
+    params.seed = seed
     if _get(cfg, 'general', 'rng'):
         params.rng = cfg['general']['rng']
 
@@ -138,9 +165,13 @@ def run(argv=None):
     ap = argparse.ArgumentParser(prog='wayne', description=__doc__.split('\n\n')[1])
     ap.add_argument('-p', dest='parameter_file', required=True)
     ap.add_argument('--max-exposures', type=int, default=None, help='stop after this many exposures')
+    ap.add_argument('--gpus', type=int, default=None,
+                    help='partition the visit exposure-wise over this many GPUs (one process each)')
     args = ap.parse_args(argv)
     with open(args.parameter_file) as f:
         cfg = yaml.safe_load(f)
+    if args.gpus and args.gpus > 1 and 'RANK' not in os.environ:
+        return _spawn_ranks(args, cfg)
     base = os.path.dirname(os.path.abspath(args.parameter_file))
     obs = build_observation(cfg, base)
     shutil.copy2(args.parameter_file, os.path.join(obs.outdir, os.path.basename(args.parameter_file)))
@@ -157,6 +188,26 @@ def run(argv=None):
     out = obs.run_observation(shard=(rank, world))
     sys.stdout.write('rank {}: wrote {} exposures to {}\n'.format(rank, len(out), obs.outdir))
     return out
+
+
+def _spawn_ranks(args, cfg):
+    """``--gpus n``: one child process per GPU, each generating its strided share of the
+    exposures; the parent only hands down the rank layout and the shared seed."""
+    import subprocess
+    seed = shared_visit_seed(_get(cfg, 'general', 'seed'))
+    cmd = [sys.executable, '-m', 'wayne_b200.run_visit', '-p', args.parameter_file]
+    if args.max_exposures:
+        cmd += ['--max-exposures', str(args.max_exposures)]
+    procs = []
+    for r in range(args.gpus):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(args.gpus),
+                   WAYNE_B200_VISIT_SEED=str(seed))
+        env.pop('MASTER_ADDR', None)
+        procs.append(subprocess.Popen(cmd, env=env))
+    rcs = [p.wait() for p in procs]
+    if any(rcs):
+        raise RuntimeError("rank exit codes {}".format(rcs))
+    return {}
 
 
 if __name__ == '__main__':
