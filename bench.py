@@ -371,8 +371,9 @@ def run_native(args, wk):
     n_warm = max(args.warmup, 8)     # long enough for the allocator pools to become stationary
     for i in range(n_warm):
         eg, _ = one(i, True)
-        phot_acc += eg._run.d_totals.sum()           # same bookkeeping as the timed loop
-        lost_acc += eg._run.lost
+        phot_acc += eg._run.thrown()                 # same bookkeeping as the timed loop
+        if eg._run.lost is not None:
+            lost_acc += eg._run.lost
         if eg._run.tally is not None:
             tally_acc += eg._run.tally
         del eg
@@ -399,8 +400,9 @@ def run_native(args, wk):
         ta = time.perf_counter()
         eg, _ = one(n_warm + i, True)
         v_issue.append((time.perf_counter() - ta) * 1e3)
-        phot_acc += eg._run.d_totals.sum()       # device-side bookkeeping, no sync
-        lost_acc += eg._run.lost
+        phot_acc += eg._run.thrown()             # device-side bookkeeping, no sync
+        if eg._run.lost is not None:
+            lost_acc += eg._run.lost
         if eg._run.tally is not None:
             tally_acc += eg._run.tally           # [binned inside the frame, dropped outside it]
         geom = eg._run.win_geometry
@@ -495,16 +497,19 @@ def run_native(args, wk):
     R = wk['nsamp'] - 1
     per = lambda name: (stages[name][0] / args.steps) if name in stages else None   # noqa: E731
     hbm_peak, peak_src = measured_peaks()
-    reads_bytes = (R * F * F * 8            # interval accumulators
-                   + 2 * R * F * F * 8      # dark, dark error
-                   + 2 * F * F * 8          # sky, gain
-                   + 4 * F * F * 8          # non-linearity planes (1+c1, c2, c3, c4; the derivative's
+    from wayne_b200 import params as _p
+    pb = 4 if (_p.use_context and _p.direct_accumulation) else 8    # resident planes: float32 through the context
+    reads_bytes = (R * F * F * 8            # interval accumulators (int64 fixed point) read ...
+                   + (R * F * F * 8 if pb == 4 else 0)   # ... and written back as zeros (no memset pass)
+                   + 2 * R * F * F * pb     # dark, dark error
+                   + 2 * F * F * pb         # sky, gain
+                   + 4 * F * F * pb         # non-linearity planes (1+c1, c2, c3, c4; the derivative's
                                             # coefficients are formed from them in the native kernel)
                    + (F * F * 8 if S == 256 else 0) + F * F * 4   # zero read, cosmic heads
-                   + (R + 1) * F * F * 8)   # NSAMP reads written
+                   + (R + 1) * F * F * 8)   # NSAMP reads written (float64 like the reference)
     t_reads, t_throw, t_gather, t_counts = per('k_reads'), per('k_throw'), per('k_gather'), per('k_counts')
     ww, wh, chunk = geom
-    gather_bytes = N * ww * wh * 4 + 2 * R * F * F * 8     # only on the window/gather (parity) path
+    gather_bytes = (N * ww * wh * 4 + 2 * R * F * F * 8) if ww else 0     # only on the window/gather (parity) path
     roof_hbm = {'kernel': 'k_reads_native', 'bound': 'hbm', 'achieved': reads_bytes / (t_reads * 1e-3) / 1e9,
                 'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': peak_src,
                 'frac': reads_bytes / (t_reads * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
@@ -551,7 +556,7 @@ def run_native(args, wk):
                   'mufu_bound_gelectron_s': (148 * 16 * (clocks['sm_mhz'] if clocks and clocks.get('sm_mhz')
                                                         else 1965.0) * 1e6 / 4) / 1e9,
                   'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
-    dominant = max(stages.items(), key=lambda kv: kv[1][0])[0]
+    dominant = max(((k, v) for k, v in stages.items() if k.startswith('k_')), key=lambda kv: kv[1][0])[0]
     line = {
         'metric': 'exposures_per_s', 'value': world * 1e3 / ms_value, 'unit': 'exposures/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_value,

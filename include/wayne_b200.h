@@ -150,6 +150,11 @@ typedef struct wb200_counts_args {
     double *d_expected;
     int32_t *d_counts;
     uint64_t *d_totals;
+    const double *d_sep_row;   /* nullable [n_samples]: SEPARABLE planet signal          */
+                               /*   depth[s][w] = d_sep_row[s] * d_depth[w]             */
+                               /* (d_depth then holds the per-bin factor, depth_ld      */
+                               /* unused): a transit of one light-curve shape times a   */
+                               /* depth spectrum, bit-identical to the dense product    */
 } wb200_counts_args;
 
 int wb200_counts_ex(const wb200_counts_args *args, void *stream);
@@ -247,7 +252,8 @@ typedef struct wb200_gather_args {
     int32_t exact;              /* 1: the reference's flat expression operation */
                                 /* for operation (fp64 divide + sqrt; parity   */
                                 /* mode); 0: hoisted reciprocals + FMAs (native)*/
-    int32_t pad0;
+    int32_t flat_planes_f32;    /* direct accumulation only: d_flat[] point at float32 */
+                                /* planes (the file's dtype) instead of float64     */
     double flat_wmin, flat_wmax;
     const int32_t *d_read_end;  /* [R] global index of each read's last sample */
     const int32_t *d_win;
@@ -297,19 +303,21 @@ typedef struct wb200_reads_args {
     int32_t fast_math;          /* 1 (native mode): fp32-SFU normals, reciprocal */
                                 /* gain; 0: fp64 expressions of the reference    */
     int32_t acc_fixed;          /* 1: d_acc is int64 fixed point (2^24 / electron) */
-    int32_t pad1;
+    int32_t zero_acc;           /* 1 (native kernel, acc_fixed): every interval-plane  */
+                                /* element is written back as 0 once it has been read, */
+                                /* so the next exposure needs no memset pass           */
     double const_gain;          /* 2.35, used when d_gain == NULL               */
     double clip_lo, clip_hi;    /* -20, 78000                                   */
     double read_noise;          /* 14.1/2.35                                    */
     const double *d_dt;         /* [R] read interval lengths, seconds           */
     const void *d_acc;          /* [R][F][F] electrons per interval: float64, or */
                                 /* int64 fixed point when acc_fixed             */
-    const double *d_sky;        /* master sky plane                             */
-    const double *d_gain;       /* 2.35/pfl plane or NULL                       */
+    const void *d_sky;          /* master sky plane (float64; float32 when planes_f32) */
+    const void *d_gain;         /* 2.35/pfl plane or NULL            (same)     */
     const double *d_zero;       /* zero read (initial bias) or NULL (= zeros)   */
-    const double *d_dark;       /* [R][F][F] or NULL                            */
-    const double *d_dark_err;   /* [R][F][F]                                    */
-    const double *d_nl[7];      /* 1+c1, c2, c3, c4, 2*c2, 3*c3, 4*c4           */
+    const void *d_dark;         /* [R][F][F] or NULL                 (same)     */
+    const void *d_dark_err;     /* [R][F][F]                         (same)     */
+    const void *d_nl[7];        /* 1+c1, c2, c3, c4, 2*c2, 3*c3, 4*c4 (same)    */
     const double *d_draw_noise; /* [R][F][F] compat: N(mu*dt, sd*dt) draws      */
     const double *d_draw_sky;   /* [R][F][F] compat: Poisson draws              */
     const double *d_draw_dark;  /* [R][F][F] compat: N(dark, err) draws         */
@@ -320,6 +328,11 @@ typedef struct wb200_reads_args {
     const double *d_cos_energy; /* [n_cosmics]                                  */
     int32_t *d_newton_iters;    /* [R] scratch for exact_newton (zeroed here)   */
     void *d_out;
+    int32_t planes_f32;         /* 1 (native kernel only): sky, gain, nl, dark and dark  */
+                                /* error planes are float32 -- the dtype of the reference's */
+                                /* calibration FITS files (grism.py:66-76, detector.py:56-57, */
+                                /* 183-190) -- promoted in registers                     */
+    int32_t pad2;
 } wb200_reads_args;
 
 int wb200_reads(const wb200_reads_args *args, void *stream);
@@ -328,6 +341,133 @@ int wb200_reads(const wb200_reads_args *args, void *stream);
  * d_head [F*F] is set to -1 and filled; d_next [n] out. */
 int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels,
                         int32_t *d_head, int32_t *d_next, void *stream);
+
+/* --------------------------------------------------------------------------
+ * Exposure-level interface: ONE call per exposure.
+ *
+ * The reference's boundary between Python and native code is one call per
+ * sub-sample (wayne/pyparallel.pyx:27-30, called from wayne/exposure_generator.py:
+ * 636-639 inside the loop :336-394).  Here the whole native-mode exposure --
+ * stage 1 tables and traces, Philox counts, the electron throw with the flat
+ * fused into the tile flush, the per-pixel ramp pass (:178-405 and :407-444) --
+ * is one call on an opaque per-GPU context that owns the resident calibration
+ * planes, the scratch buffers and the staging of the small per-exposure inputs.
+ * A C / C++ host needs nothing but this section.
+ *
+ * Rules: one context per (GPU, instrument configuration); calls on ONE context
+ * must be serialised by the caller (distinct contexts may be used from distinct
+ * threads; ctypes releases the GIL).  Every call returns WB200_OK or a negative
+ * status; wb200_ctx_last_error(ctx) (or wb200_last_error() on the calling
+ * thread) has the message.  Nothing throws across the boundary.
+ * wb200_exposure_run is asynchronous on `stream`: it returns when the work is
+ * queued.  Host arrays passed to it are copied before it returns and may be
+ * reused immediately.
+ * -------------------------------------------------------------------------- */
+typedef struct wb200_ctx wb200_ctx;
+
+typedef struct wb200_instrument {
+    int32_t subarray;           /* SUBARRAY                                          */
+    int32_t L, F, border;       /* light-sensitive side, full side (detector.py:102-124), 5 */
+    int32_t flat_off;           /* (1014 - SUBARRAY) floor-div 2 (grism.py:361-363)  */
+    int32_t flat_n;             /* side of the flat-field planes                     */
+    int32_t flat_f32;           /* 1: flat value rounded to float32 (grism.py:380-385) */
+    int32_t n_sens;             /* length of the sensitivity table                   */
+    double sub_scale;           /* 507 - SUBARRAY//2 (exposure_generator.py:630)     */
+    double flat_wmin, flat_wmax;
+    double psf_poly12[12];      /* grism.py:85-90: ratio, sigma_l, sigma_h (highest power first) */
+    double trace_coeff9[9];     /* grism.py:756-776                                  */
+    double wl_sol9[9];
+    double const_gain;          /* 2.35 (detector.py:29)                             */
+    double clip_lo, clip_hi;    /* -20, 78000 (detector.py:26-27)                    */
+    double read_noise;          /* 14.1 / 2.35 (detector.py:33)                      */
+} wb200_instrument;
+
+/* Resident calibration planes.  Image planes are held in float32 -- the dtype of
+ * the reference's calibration FITS files (grism.py:66-76, 411-423; detector.py:
+ * 56-57, 183-190, 200-209) -- in the bordered F x F layout (light-sensitive pixel
+ * (r, c) at (r + border, c + border)); float64 input is accepted when every value
+ * is float32-representable (anything else would change results and is refused).
+ * ZERO (the initial bias, a float64 file) and the sensitivity table stay float64. */
+#define WB200_PLANE_FLAT0 0     /* f0..f3 [flat_n][flat_n]                           */
+#define WB200_PLANE_FLAT1 1
+#define WB200_PLANE_FLAT2 2
+#define WB200_PLANE_FLAT3 3
+#define WB200_PLANE_SKY 4       /* master sky [F][F]                                 */
+#define WB200_PLANE_GAIN 5      /* 2.35 / pfl [F][F], 1 in the border                */
+#define WB200_PLANE_NL0 6       /* 1 + c1, c2, c3, c4 [F][F] (detector.py:328-343)   */
+#define WB200_PLANE_NL1 7
+#define WB200_PLANE_NL2 8
+#define WB200_PLANE_NL3 9
+#define WB200_PLANE_DARK 10     /* [n_reads][F][F]: read r uses super-dark NSAMP r+2 */
+#define WB200_PLANE_DARK_ERR 11 /* [n_reads][F][F], non-positive entries already 1e-5 */
+#define WB200_PLANE_ZERO 12     /* zero read / initial bias [F][F] float64           */
+#define WB200_PLANE_SENS_WL 13  /* [n_sens] microns, float64                         */
+#define WB200_PLANE_SENS_VAL 14 /* [n_sens] float64                                  */
+#define WB200_PLANE_COUNT 15
+#define WB200_F32 0
+#define WB200_F64 1
+
+int wb200_ctx_create(int device, wb200_ctx **ctx_out);
+int wb200_ctx_destroy(wb200_ctx *ctx);
+const char *wb200_ctx_last_error(const wb200_ctx *ctx);
+int wb200_ctx_set_instrument(wb200_ctx *ctx, const wb200_instrument *inst);
+/* host -> device, synchronous; replaces a plane uploaded before.  host = NULL drops it. */
+int wb200_ctx_upload_plane(wb200_ctx *ctx, int which, const void *host, int dtype, int64_t count);
+
+typedef struct wb200_exposure_args {
+    int32_t n_samples, n_bins, n_reads;   /* N, W, R = NSAMP - 1                     */
+    int32_t count_mode;         /* WB200_COUNT_ROUND | WB200_COUNT_POISSON (exposure_generator.py:625-628) */
+    int32_t cheb_order;         /* > 0: planet signal as Chebyshev coefficients (see wb200_counts_ex) */
+    int32_t n_cosmics;
+    int32_t add_flat, add_sky, add_gain, add_dark, add_nonlinear, clip, add_read_noise,
+        add_zero, add_noise;    /* the switches of scanning_frame (exposure_generator.py:178-192) */
+    int32_t out_f32;            /* 0: float64 reads like the reference, 1: float32   */
+    uint32_t key0, key1;        /* Philox key of the exposure                        */
+    int32_t pad0;
+    double scale;               /* visit-trend scale factor (:620-621)               */
+    double sky_rate;            /* counts/s                                          */
+    double noise_mean, noise_std;
+    int64_t depth_ld;           /* row stride of d_depth                             */
+    /* small HOST arrays (copied before the call returns) */
+    const double *wl;           /* [W] microns, cropped to the grism limits          */
+    const double *flux;         /* [W] or NULL when d_flux is given                  */
+    const double *xref, *yref;  /* [N] sub-sample reference positions (jitter, scan) */
+    const double *dur_ms;       /* [N] sub-sample durations                          */
+    const double *dt_s;         /* [R] read interval lengths                         */
+    const int32_t *read_end;    /* [R] index of the last sub-sample of each read     */
+    const double *cheb_x;       /* [W] or NULL                                       */
+    const double *cheb_coef;    /* HOST [N][cheb_order], or NULL when d_cheb_coef    */
+    const double *sep_row;      /* separable planet signal (see wb200_counts_args):  */
+    const double *sep_col;      /* HOST [N] and [W]; both NULL otherwise             */
+    const int32_t *cos_pixel;   /* [n_cosmics] bordered flat pixel index             */
+    const int32_t *cos_read;    /* [n_cosmics] read interval                         */
+    const double *cos_energy;   /* [n_cosmics] electrons                             */
+    /* large inputs already on the device (nullable) */
+    const double *d_depth;      /* planet signal [N][depth_ld] (first used column)   */
+    const double *d_cheb_coef;  /* [N][cheb_order]                                   */
+    const double *d_flux;       /* [W]                                               */
+    uint64_t *d_stats;          /* nullable device [4], written: electrons thrown,   */
+                                /* binned inside the frame, dropped outside it, 0    */
+} wb200_exposure_args;
+
+/* d_out: device [n_reads+1][F][F] float64 (float32 when out_f32), read 0 = zero read. */
+int wb200_exposure_run(wb200_ctx *ctx, const wb200_exposure_args *args, void *d_out, void *stream);
+
+/* Diagnostics / parity tests: geometry chosen for the last exposure and synchronous
+ * copies of the context's scratch buffers to the host.
+ *   info[0] = bins per CTA of the thrower, [1] = staging slots in use, [2] = exposures run,
+ *   [3] = kernels launched by the last exposure.
+ *   which: 0 counts int32 [N][W]; 1 totals uint64 [N]; 2 trace float64 [N][8];
+ *          3 tables float64 [5][W] (ratio, sigma_l, sigma_h, sens, dwl) */
+int wb200_ctx_info(const wb200_ctx *ctx, int64_t info[8]);
+/* Per-stage device timing for the bench: with profiling on, wb200_exposure_run brackets its
+ * stages with CUDA events on the launching stream (no synchronisation).  wb200_ctx_stage_times
+ * synchronises the device, returns the accumulated milliseconds and launch-group counts since
+ * the last call and resets them.  Stages: 0 tables + traces, 1 counts, 2 cosmic chains,
+ * 3 electron throw (+ flat + accumulation), 4 per-pixel ramp pass. */
+int wb200_ctx_profile(wb200_ctx *ctx, int enable);
+int wb200_ctx_stage_times(wb200_ctx *ctx, double ms_out[8], int64_t n_out[8]);
+int wb200_ctx_read_scratch(wb200_ctx *ctx, int which, void *host_out, int64_t bytes);
 
 /* Microbenchmarks used for the roofline denominators (profiles/).  which:
  *   0..3  shared-memory atomics (same address / conflict-free / PSF-like 3x3 / random)

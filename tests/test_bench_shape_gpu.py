@@ -91,7 +91,7 @@ def test_c4_native_conserves_every_electron(calb_dir):
     wk, inp = _workload(calb_dir, 1.0e9)
     eg, planes, _ = _native(inp, wk, (1963, 77), add_flat=False)
     run = eg._run
-    counts = run.d_counts.cpu().numpy().astype(np.int64)
+    counts = run.counts_host().astype(np.int64)
     assert counts.shape == (4116, 4096) and 9.7e8 < counts.sum() < 1.03e9
     assert run.win_geometry[2] == 1376
     ints = np.rint(planes)
@@ -115,7 +115,7 @@ def test_c4_native_pixels_match_analytic_expectation(calb_dir):
     eg, planes, kw = _native(inp, wk, (1963, 78), add_flat=True)
     run = eg._run
     cal = harness.oracle_calibration('G141', dark_mode=None)
-    counts = run.d_counts.cpu().numpy()
+    counts = run.counts_host()
     # the exposure's own sub-sample reference positions, restated: native-mode jitter stream
     # (exposure_generator.py) + scan, then the oracle's trace for every sub-sample
     key = (1963, 78)

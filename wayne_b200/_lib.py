@@ -52,6 +52,7 @@ class CountsArgs(C.Structure):
         ("d_flux", c_void_p), ("d_depth", c_void_p), ("d_cheb_coef", c_void_p), ("d_cheb_x", c_void_p),
         ("d_sens", c_void_p), ("d_dwl", c_void_p), ("d_dur_ms", c_void_p),
         ("d_expected", c_void_p), ("d_counts", c_void_p), ("d_totals", c_void_p),
+        ("d_sep_row", c_void_p),
     ]
 
 
@@ -61,7 +62,7 @@ class GatherArgs(C.Structure):
         ("L", c_i32), ("F", c_i32), ("border", c_i32),
         ("win_w", c_i32), ("win_h", c_i32),
         ("add_flat", c_i32), ("flat_off", c_i32), ("flat_n", c_i32),
-        ("flat_f32", c_i32), ("exact", c_i32), ("pad0", c_i32),
+        ("flat_f32", c_i32), ("exact", c_i32), ("flat_planes_f32", c_i32),
         ("flat_wmin", c_double), ("flat_wmax", c_double),
         ("d_read_end", c_void_p), ("d_win", c_void_p), ("d_win_ox", c_void_p),
         ("d_win_oy", c_void_p), ("d_trace", c_void_p),
@@ -78,7 +79,7 @@ class ReadsArgs(C.Structure):
         ("exact_newton", c_i32), ("n_cosmics", c_i32),
         ("key0", c_u32), ("key1", c_u32),
         ("noise_mean", c_double), ("noise_std", c_double), ("sky_rate", c_double),
-        ("sky_f32", c_i32), ("fast_math", c_i32), ("acc_fixed", c_i32), ("pad1", c_i32),
+        ("sky_f32", c_i32), ("fast_math", c_i32), ("acc_fixed", c_i32), ("zero_acc", c_i32),
         ("const_gain", c_double), ("clip_lo", c_double), ("clip_hi", c_double),
         ("read_noise", c_double),
         ("d_dt", c_void_p), ("d_acc", c_void_p), ("d_sky", c_void_p), ("d_gain", c_void_p),
@@ -90,8 +91,41 @@ class ReadsArgs(C.Structure):
         ("d_cos_energy", c_void_p),
         ("d_newton_iters", c_void_p),
         ("d_out", c_void_p),
+        ("planes_f32", c_i32), ("pad2", c_i32),
     ]
 
+
+class Instrument(C.Structure):
+    _fields_ = [
+        ("subarray", c_i32), ("L", c_i32), ("F", c_i32), ("border", c_i32),
+        ("flat_off", c_i32), ("flat_n", c_i32), ("flat_f32", c_i32), ("n_sens", c_i32),
+        ("sub_scale", c_double), ("flat_wmin", c_double), ("flat_wmax", c_double),
+        ("psf_poly12", c_double * 12), ("trace_coeff9", c_double * 9), ("wl_sol9", c_double * 9),
+        ("const_gain", c_double), ("clip_lo", c_double), ("clip_hi", c_double), ("read_noise", c_double),
+    ]
+
+
+class ExposureArgs(C.Structure):
+    _fields_ = [
+        ("n_samples", c_i32), ("n_bins", c_i32), ("n_reads", c_i32),
+        ("count_mode", c_i32), ("cheb_order", c_i32), ("n_cosmics", c_i32),
+        ("add_flat", c_i32), ("add_sky", c_i32), ("add_gain", c_i32), ("add_dark", c_i32),
+        ("add_nonlinear", c_i32), ("clip", c_i32), ("add_read_noise", c_i32), ("add_zero", c_i32),
+        ("add_noise", c_i32), ("out_f32", c_i32),
+        ("key0", c_u32), ("key1", c_u32), ("pad0", c_i32),
+        ("scale", c_double), ("sky_rate", c_double), ("noise_mean", c_double), ("noise_std", c_double),
+        ("depth_ld", c_i64),
+        ("wl", c_void_p), ("flux", c_void_p), ("xref", c_void_p), ("yref", c_void_p), ("dur_ms", c_void_p),
+        ("dt_s", c_void_p), ("read_end", c_void_p), ("cheb_x", c_void_p), ("cheb_coef", c_void_p),
+        ("sep_row", c_void_p), ("sep_col", c_void_p),
+        ("cos_pixel", c_void_p), ("cos_read", c_void_p), ("cos_energy", c_void_p),
+        ("d_depth", c_void_p), ("d_cheb_coef", c_void_p), ("d_flux", c_void_p), ("d_stats", c_void_p),
+    ]
+
+
+(PLANE_FLAT0, PLANE_FLAT1, PLANE_FLAT2, PLANE_FLAT3, PLANE_SKY, PLANE_GAIN, PLANE_NL0, PLANE_NL1, PLANE_NL2,
+ PLANE_NL3, PLANE_DARK, PLANE_DARK_ERR, PLANE_ZERO, PLANE_SENS_WL, PLANE_SENS_VAL) = range(15)
+F32, F64 = 0, 1
 
 # every symbol include/wayne_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -120,6 +154,16 @@ SIGNATURES = {
     "wb200_throw_photons_direct": (c_int, [C.POINTER(PhotonArgs), C.POINTER(GatherArgs), c_int, c_void_p]),
     "wb200_reads": (c_int, [C.POINTER(ReadsArgs), c_void_p]),
     "wb200_cosmic_chains": (c_int, [c_int, c_void_p, c_i32, c_void_p, c_void_p, c_void_p]),
+    "wb200_ctx_create": (c_int, [c_int, C.POINTER(c_void_p)]),
+    "wb200_ctx_destroy": (c_int, [c_void_p]),
+    "wb200_ctx_last_error": (C.c_char_p, [c_void_p]),
+    "wb200_ctx_set_instrument": (c_int, [c_void_p, C.POINTER(Instrument)]),
+    "wb200_ctx_upload_plane": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64]),
+    "wb200_exposure_run": (c_int, [c_void_p, C.POINTER(ExposureArgs), c_void_p, c_void_p]),
+    "wb200_ctx_info": (c_int, [c_void_p, C.POINTER(c_i64)]),
+    "wb200_ctx_profile": (c_int, [c_void_p, c_int]),
+    "wb200_ctx_stage_times": (c_int, [c_void_p, DP, C.POINTER(c_i64)]),
+    "wb200_ctx_read_scratch": (c_int, [c_void_p, c_int, c_void_p, c_i64]),
     "wb200_microbench": (c_int, [c_int, c_int, DP, DP]),
     "wb200_philox_words": (c_int, [c_int, C.POINTER(c_u32), C.POINTER(c_u32), C.POINTER(c_u32)]),
 }

@@ -128,7 +128,8 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
                 long long depth_ld, const double *__restrict__ cheb_coef, int cheb_order,
                 const double *__restrict__ cheb_x, const double *__restrict__ sens,
                 const double *__restrict__ dwl, const double *__restrict__ dur_ms, double scale,
-                uint32_t k0, uint32_t k1, double *expected, int *counts, unsigned long long *totals)
+                uint32_t k0, uint32_t k1, double *expected, int *counts, unsigned long long *totals,
+                const double *__restrict__ sep_row)
 {
     extern __shared__ float s_cdf[]; // [CW_T][CW_THREADS]
     const int w = blockIdx.x * CW_THREADS + threadIdx.x;
@@ -137,8 +138,10 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
     const bool live = w < W;
     float *tbl = s_cdf + threadIdx.x;
     double f0 = 0.0, sn = 0.0, dw = 0.0, x = 0.0;
-    const bool use_depth = live && !cheb_coef && depth;
-    double dnext = 0.0;
+    // separable planet signal depth[s][w] = sep_row[s] * depth[w] (depth = the per-bin factor)
+    const bool use_sep = live && !cheb_coef && depth && sep_row;
+    const bool use_depth = live && !cheb_coef && depth && !sep_row;
+    double dnext = 0.0, sep_col = 0.0;
     if (live) {
         f0 = flux[w];
         sn = sens[w];
@@ -147,6 +150,8 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
             x = cheb_x[w];
         if (use_depth)
             dnext = depth[(size_t)s0 * depth_ld + w];
+        if (use_sep)
+            sep_col = depth[w];
     }
     CountWindow win;
     win.lam = -1.0f;
@@ -177,6 +182,8 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
                 f = f * (1. - d);
             } else if (use_depth)
                 f = f * (1. - dcur);
+            else if (use_sep)
+                f = f * (1. - sep_col * sep_row[s]);
             // the unit algebra of k_counts (exposure_generator.py:602-623), same order
             double e = f * sn;
             e = e * dw;

@@ -98,9 +98,11 @@ struct PhiloxStream {
     uint32_t k0, k1, cy, cz, cw, cx;
     uint4 buf;
     int have;
+    // `first` = first block counter of the stream (blocks below it belong to other users of the
+    // same (minor, major, stream) triple: the per-pair call of the read kernels is block 1)
     __device__ __forceinline__ PhiloxStream(uint32_t k0_, uint32_t k1_, uint32_t minor,
-                                            uint32_t major, uint32_t stream)
-        : k0(k0_), k1(k1_), cy(minor), cz(major), cw(stream), cx(0), have(0)
+                                            uint32_t major, uint32_t stream, uint32_t first = 0)
+        : k0(k0_), k1(k1_), cy(minor), cz(major), cw(stream), cx(first), have(0)
     {
     }
     __device__ __forceinline__ uint32_t next()

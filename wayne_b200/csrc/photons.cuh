@@ -606,8 +606,11 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
             Yi += ga.flat_n;
         if ((unsigned)Xi < (unsigned)ga.flat_n && (unsigned)Yi < (unsigned)ga.flat_n) {
             const size_t fi = (size_t)Yi * ga.flat_n + Xi;
-            double fv = flat_value_fast(d.g, (double)Xi, (double)Yi, ga.d_flat[0][fi], ga.d_flat[1][fi],
-                                        ga.d_flat[2][fi], ga.d_flat[3][fi], ga.flat_wmin, d.inv_range);
+            double f[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                f[i] = ga.flat_planes_f32 ? (double)reinterpret_cast<const float *>(ga.d_flat[i])[fi] : ga.d_flat[i][fi];
+            double fv = flat_value_fast(d.g, (double)Xi, (double)Yi, f[0], f[1], f[2], f[3], ga.flat_wmin, d.inv_range);
             if (ga.flat_f32)
                 fv = (double)__double2float_rn(fv);
             v *= fv;

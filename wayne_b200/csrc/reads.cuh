@@ -107,9 +107,9 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
     if (valid) {
         if (PASS != 2) {
             if (a.add_sky && !a.d_draw_sky)
-                load_pair(a.d_sky, p, sky);
+                load_pair(reinterpret_cast<const double *>(a.d_sky), p, sky);
             if (a.d_gain)
-                load_pair(a.d_gain, p, gain);
+                load_pair(reinterpret_cast<const double *>(a.d_gain), p, gain);
             if (a.d_cos_head) {
                 const int2 t = *reinterpret_cast<const int2 *>(a.d_cos_head + p);
                 chead[0] = t.x;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
         if (a.add_nonlinear) {
             double t[7][2];
             for (int i = 0; i < 7; ++i)
-                load_pair(a.d_nl[i], p, t[i]);
+                load_pair(reinterpret_cast<const double *>(a.d_nl[i]), p, t[i]);
             for (int h = 0; h < 2; ++h)
                 nl[h] = NLCoef{t[0][h], t[1][h], t[2][h], t[3][h], t[4][h], t[5][h], t[6][h]};
         }
@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                             if (a.d_draw_sky) {
                                 px = px + ds[h];
                             } else {
-                                PhiloxStream g(a.key0, a.key1, pid, (uint32_t)r, WB_STREAM_SKY);
+                                // FAST: block 1 of pixel p is the pair's shared call `qs` above (its z, w feed
+                                // the dark normals): the large-mean sampler's own blocks start at 2, as in
+                                // reads_native.cuh, so no word serves two noise terms
+                                PhiloxStream g(a.key0, a.key1, pid, (uint32_t)r, WB_STREAM_SKY, FAST ? 2u : 0u);
                                 const double bg = a.sky_rate * dt;
                                 const double lam = a.sky_f32
                                     ? (double)__fmul_rn(__double2float_rn(sky[h]), __double2float_rn(bg))
@@ -221,8 +224,8 @@ __global__ void __launch_bounds__(256) k_reads(const wb200_reads_args a)
                         v[1] = v[1] + dd[1];
                     } else {
                         double dk[2], de[2];
-                        load_pair(a.d_dark + (size_t)r * plane, p, dk);
-                        load_pair(a.d_dark_err + (size_t)r * plane, p, de);
+                        load_pair(reinterpret_cast<const double *>(a.d_dark) + (size_t)r * plane, p, dk);
+                        load_pair(reinterpret_cast<const double *>(a.d_dark_err) + (size_t)r * plane, p, de);
                         double z[2];
                         if (FAST) {
                             box_muller_fd(qs.z, qs.w, z[0], z[1]);

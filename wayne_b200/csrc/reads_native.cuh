@@ -193,7 +193,24 @@ __device__ __forceinline__ double newton_native(double p, const NLCoef4 &k)
     return u;
 }
 
-template <bool OUT32>
+// a pair of adjacent plane values promoted to double: PLANES32 = the planes are held in the
+// calibration files' own float32 (every product the reference forms with them -- float32 sky x
+// rate, float32 2.35 / pfl, float32 1 + c1, the float32 dark-error floor -- is float32-valued, so
+// the promotion is exact and half the bytes move)
+template <bool PLANES32>
+__device__ __forceinline__ double2 ld_plane2(const void *base, size_t idx)
+{
+    if (PLANES32) {
+        float2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(r.x), "=f"(r.y)
+                     : "l"(reinterpret_cast<const float *>(base) + idx));
+        return make_double2((double)r.x, (double)r.y);
+    }
+    return ld_stream2(reinterpret_cast<const double *>(base) + idx);
+}
+
+template <bool OUT32, bool PLANES32>
 __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_reads_args a)
 {
     extern __shared__ float s_sky[]; // [SKY_T][2][RN_THREADS] floats, then [10][RN_THREADS] doubles
@@ -217,14 +234,14 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
     // ---- per-pixel constants -------------------------------------------------
     double ginv[2] = {1.0 / a.const_gain, 1.0 / a.const_gain};
     if (a.d_gain) {
-        const double2 g = ld_stream2(a.d_gain + p);
+        const double2 g = ld_plane2<PLANES32>(a.d_gain, p);
         ginv[0] = 1.0 / g.x;
         ginv[1] = 1.0 / g.y;
     }
     float skyf[2] = {0.f, 0.f};
     double skyd[2] = {0., 0.};
     if (sky_on) {
-        const double2 s = ld_stream2(a.d_sky + p);
+        const double2 s = ld_plane2<PLANES32>(a.d_sky, p);
         skyd[0] = s.x;
         skyd[1] = s.y;
         skyf[0] = __double2float_rn(s.x);
@@ -255,7 +272,7 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
     if (a.add_nonlinear) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double2 t = ld_stream2(a.d_nl[i] + p);
+            const double2 t = ld_plane2<PLANES32>(a.d_nl[i], p);
             sc[(2 * i) * RN_THREADS] = t.x;
             sc[(2 * i + 1) * RN_THREADS] = t.y;
         }
@@ -274,13 +291,17 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
     auto issue = [&](int r) {
         const size_t off = (size_t)r * plane + p;
         ndt = a.d_dt[r];
-        if (acc_fixed)
-            nq = *reinterpret_cast<const longlong2 *>(reinterpret_cast<const long long *>(a.d_acc) + off);
-        else
+        if (acc_fixed) {
+            longlong2 *q = reinterpret_cast<longlong2 *>(
+                reinterpret_cast<long long *>(const_cast<void *>(a.d_acc)) + off);
+            nq = *q;
+            if (a.zero_acc) // the interval planes are left zeroed for the next exposure (no memset pass)
+                *q = make_longlong2(0, 0);
+        } else
             nacc = ld_stream2(reinterpret_cast<const double *>(a.d_acc) + off);
         if (dark_on) {
-            ndk = ld_stream2(a.d_dark + off);
-            nde = ld_stream2(a.d_dark_err + off);
+            ndk = ld_plane2<PLANES32>(a.d_dark, off);
+            nde = ld_plane2<PLANES32>(a.d_dark_err, off);
         }
     };
     issue(0);

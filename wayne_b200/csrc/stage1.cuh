@@ -186,14 +186,17 @@ k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict
          long long depth_ld, const double *__restrict__ cheb_coef, int cheb_order,
          const double *__restrict__ cheb_x, const double *__restrict__ sens,
          const double *__restrict__ dwl, const double *__restrict__ dur_ms, double scale, int mode,
-         uint32_t k0, uint32_t k1, double *expected, int *counts, unsigned long long *totals)
+         uint32_t k0, uint32_t k1, double *expected, int *counts, unsigned long long *totals,
+         const double *__restrict__ sep_row)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int s0 = blockIdx.y * COUNTS_SPT;
     const bool live = w < W;
     double f0 = 0.0, sn = 0.0, dw = 0.0, x = 0.0;
-    const bool use_depth = live && !cheb_coef && depth;
-    double dnext = 0.0;
+    // separable planet signal depth[s][w] = sep_row[s] * depth[w] (depth = the per-bin factor)
+    const bool use_sep = live && !cheb_coef && depth && sep_row;
+    const bool use_depth = live && !cheb_coef && depth && !sep_row;
+    double dnext = 0.0, sep_col = 0.0;
     if (live) {
         f0 = flux[w];
         sn = sens[w];
@@ -202,6 +205,8 @@ k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict
             x = cheb_x[w];
         if (use_depth && s0 < N)
             dnext = depth[(size_t)s0 * depth_ld + w];
+        if (use_sep)
+            sep_col = depth[w];
     }
 #pragma unroll 1
     for (int i = 0; i < COUNTS_SPT; ++i) {
@@ -231,8 +236,10 @@ k_counts(int N, int W, const double *__restrict__ flux, const double *__restrict
                     d = c0 + c1 * x;
                 }
                 f = f * (1. - d);
-            } else if (depth)
+            } else if (use_depth)
                 f = f * (1. - dcur);
+            else if (use_sep)
+                f = f * (1. - sep_col * sep_row[s]);
             double e = f * sn;       // ph / s / angstrom
             e = e * dw;              // (ph/s/A) * micron
             e = e * 1e4;             // micron -> angstrom : ph / s

@@ -62,8 +62,7 @@ static int launch_throw(const PhotonParams &p, cudaStream_t st)
     return WB200_OK;
 }
 
-static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st,
-                         const wb200_gather_args *direct = nullptr)
+int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct)
 {
     WB_REQUIRE(a != nullptr, "null args");
     WB_REQUIRE(a->n_samples >= 0 && a->n_bins > 0, "bad sizes");
@@ -110,6 +109,101 @@ static int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t s
     default:
         return fail(WB200_ERR_ARG, "unknown rng_mode%s%s");
     }
+}
+int launch_counts(const wb200_counts_args *a, cudaStream_t st)
+{
+    WB_REQUIRE(a != nullptr, "null args");
+    WB_REQUIRE(a->n_samples > 0 && a->n_samples <= 65535 && a->n_bins > 0, "bad sizes");
+    WB_REQUIRE(a->d_flux && a->d_sens && a->d_dwl && a->d_dur_ms && a->d_totals, "null buffer");
+    WB_REQUIRE(a->count_mode >= 0 && a->count_mode <= 2, "bad count_mode");
+    WB_REQUIRE(a->count_mode == WB200_COUNT_NONE || a->d_counts, "counts output needed");
+    WB_REQUIRE(!a->d_cheb_coef || (a->d_cheb_x && a->cheb_order >= 1 && a->cheb_order <= 32),
+               "Chebyshev planet signal: need x and 1 <= order <= 32");
+    WB_CUDA(cudaMemsetAsync(a->d_totals, 0, sizeof(uint64_t) * a->n_samples, st));
+    if (a->count_mode == WB200_COUNT_POISSON && !getenv("WB200_GENERIC_COUNTS")) {
+        // native mode: CDF-window sampler, a thread owns a bin for CW_BLOCK sub-samples
+        static_assert(CW_BLOCK % 2 == 0, "Philox words are shared by sub-sample pairs");
+        dim3 wgrid((a->n_bins + CW_THREADS - 1) / CW_THREADS, (a->n_samples + CW_BLOCK - 1) / CW_BLOCK);
+        k_counts_window<<<wgrid, CW_THREADS, sizeof(float) * CW_T * CW_THREADS, st>>>(
+            a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld, a->d_cheb_coef,
+            a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl, a->d_dur_ms, a->scale, a->key0, a->key1,
+            a->d_expected, a->d_counts, (unsigned long long *)a->d_totals, a->d_sep_row);
+        WB_LAUNCHED("k_counts_window");
+        return WB200_OK;
+    }
+    dim3 grid((a->n_bins + COUNTS_THREADS - 1) / COUNTS_THREADS, (a->n_samples + COUNTS_SPT - 1) / COUNTS_SPT);
+    k_counts<<<grid, COUNTS_THREADS, 0, st>>>(a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld,
+                                   a->d_cheb_coef, a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl,
+                                   a->d_dur_ms, a->scale, a->count_mode, a->key0, a->key1, a->d_expected,
+                                   a->d_counts, (unsigned long long *)a->d_totals, a->d_sep_row);
+    WB_LAUNCHED("k_counts");
+    return WB200_OK;
+}
+
+
+int launch_reads(const wb200_reads_args *a, cudaStream_t st)
+{
+    WB_REQUIRE(a != nullptr, "null args");
+    WB_REQUIRE(a->n_reads >= 1 && a->n_reads <= 15, "1 <= n_reads <= 15");
+    WB_REQUIRE(a->F > 2 * a->border && (a->F % 2) == 0, "F must be even and > 2*border");
+    WB_REQUIRE(a->d_dt && a->d_acc && a->d_out, "null buffer");
+    WB_REQUIRE(!a->add_sky || a->d_sky || a->d_draw_sky, "sky plane missing");
+    WB_REQUIRE(!a->add_dark || a->d_draw_dark || (a->d_dark && a->d_dark_err), "dark planes missing");
+    if (a->add_nonlinear)
+        for (int i = 0; i < (a->planes_f32 ? 4 : 7); ++i)
+            WB_REQUIRE(a->d_nl[i], "non-linearity planes missing");
+    WB_REQUIRE(!a->d_cos_head || a->n_cosmics == 0 || (a->d_cos_next && a->d_cos_read && a->d_cos_energy),
+               "cosmic lists missing");
+    WB_REQUIRE(!a->zero_acc || a->acc_fixed, "zero_acc applies to the fixed-point interval planes");
+    const size_t pairs = (size_t)a->F * a->F / 2;
+    const int blocks = (int)((pairs + 255) / 256);
+    const bool native = a->fast_math && !a->d_draw_noise && !a->d_draw_sky && !a->d_draw_dark && !a->d_draw_rn &&
+                        !(a->exact_newton && a->add_nonlinear) &&
+                        (a->planes_f32 || (!getenv("WB200_EXACT_READS") && !getenv("WB200_GENERIC_READS")));
+    WB_REQUIRE(native || !a->planes_f32, "float32 planes are read by the native kernel only");
+    if (native) {
+        // native mode without host-drawn planes: the throughput kernel (reads_native.cuh)
+        static const size_t smem = RN_SMEM;
+        static const cudaError_t attr[4] = {
+            cudaFuncSetAttribute(k_reads_native<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            cudaFuncSetAttribute(k_reads_native<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            cudaFuncSetAttribute(k_reads_native<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            cudaFuncSetAttribute(k_reads_native<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)};
+        for (cudaError_t e : attr)
+            WB_CUDA(e);
+        const int nblocks = (int)((pairs + RN_THREADS - 1) / RN_THREADS);
+        if (a->planes_f32) {
+            if (a->out_f32)
+                k_reads_native<true, true><<<nblocks, RN_THREADS, smem, st>>>(*a);
+            else
+                k_reads_native<false, true><<<nblocks, RN_THREADS, smem, st>>>(*a);
+        } else {
+            if (a->out_f32)
+                k_reads_native<true, false><<<nblocks, RN_THREADS, smem, st>>>(*a);
+            else
+                k_reads_native<false, false><<<nblocks, RN_THREADS, smem, st>>>(*a);
+        }
+        WB_LAUNCHED("k_reads_native");
+        return WB200_OK;
+    }
+    if (a->exact_newton && a->add_nonlinear) {
+        WB_REQUIRE(!a->out_f32, "exact_newton needs the float64 output");
+        WB_REQUIRE(a->d_newton_iters, "newton scratch missing");
+        WB_CUDA(cudaMemsetAsync(a->d_newton_iters, 0, sizeof(int32_t) * 16, st));
+        k_reads<1><<<blocks, 256, 0, st>>>(*a);
+        WB_LAUNCHED("k_reads<1>");
+        k_reads<2><<<blocks, 256, 0, st>>>(*a);
+        WB_LAUNCHED("k_reads<2>");
+    } else {
+        if (a->fast_math && !getenv("WB200_EXACT_READS"))
+            k_reads<0, true><<<blocks, 256, 0, st>>>(*a);
+        else
+            k_reads<0, false><<<blocks, 256, 0, st>>>(*a);
+        WB_LAUNCHED("k_reads<0>");
+    }
+    if (a->zero_acc) // the generic kernels do not write the planes back
+        WB_CUDA(cudaMemsetAsync(const_cast<void *>(a->d_acc), 0, sizeof(long long) * (size_t)a->n_reads * a->F * a->F, st));
+    return WB200_OK;
 }
 } // namespace wb
 
@@ -191,36 +285,7 @@ int wb200_trace_positions(int n_samples, int n_bins, const double *d_trace, cons
     return WB200_OK;
 }
 
-int wb200_counts_ex(const wb200_counts_args *a, void *stream)
-{
-    WB_REQUIRE(a != nullptr, "null args");
-    WB_REQUIRE(a->n_samples > 0 && a->n_samples <= 65535 && a->n_bins > 0, "bad sizes");
-    WB_REQUIRE(a->d_flux && a->d_sens && a->d_dwl && a->d_dur_ms && a->d_totals, "null buffer");
-    WB_REQUIRE(a->count_mode >= 0 && a->count_mode <= 2, "bad count_mode");
-    WB_REQUIRE(a->count_mode == WB200_COUNT_NONE || a->d_counts, "counts output needed");
-    WB_REQUIRE(!a->d_cheb_coef || (a->d_cheb_x && a->cheb_order >= 1 && a->cheb_order <= 32),
-               "Chebyshev planet signal: need x and 1 <= order <= 32");
-    cudaStream_t st = (cudaStream_t)stream;
-    WB_CUDA(cudaMemsetAsync(a->d_totals, 0, sizeof(uint64_t) * a->n_samples, st));
-    if (a->count_mode == WB200_COUNT_POISSON && !getenv("WB200_GENERIC_COUNTS")) {
-        // native mode: CDF-window sampler, a thread owns a bin for CW_BLOCK sub-samples
-        static_assert(CW_BLOCK % 2 == 0, "Philox words are shared by sub-sample pairs");
-        dim3 wgrid((a->n_bins + CW_THREADS - 1) / CW_THREADS, (a->n_samples + CW_BLOCK - 1) / CW_BLOCK);
-        k_counts_window<<<wgrid, CW_THREADS, sizeof(float) * CW_T * CW_THREADS, st>>>(
-            a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld, a->d_cheb_coef,
-            a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl, a->d_dur_ms, a->scale, a->key0, a->key1,
-            a->d_expected, a->d_counts, (unsigned long long *)a->d_totals);
-        WB_LAUNCHED("k_counts_window");
-        return WB200_OK;
-    }
-    dim3 grid((a->n_bins + COUNTS_THREADS - 1) / COUNTS_THREADS, (a->n_samples + COUNTS_SPT - 1) / COUNTS_SPT);
-    k_counts<<<grid, COUNTS_THREADS, 0, st>>>(a->n_samples, a->n_bins, a->d_flux, a->d_depth, (long long)a->depth_ld,
-                                   a->d_cheb_coef, a->cheb_order, a->d_cheb_x, a->d_sens, a->d_dwl,
-                                   a->d_dur_ms, a->scale, a->count_mode, a->key0, a->key1, a->d_expected,
-                                   a->d_counts, (unsigned long long *)a->d_totals);
-    WB_LAUNCHED("k_counts");
-    return WB200_OK;
-}
+int wb200_counts_ex(const wb200_counts_args *a, void *stream) { return launch_counts(a, (cudaStream_t)stream); }
 
 int wb200_counts(int n_samples, int n_bins, const double *d_flux, const double *d_depth,
                  int64_t depth_ld, const double *d_sens, const double *d_dwl,
@@ -278,14 +343,14 @@ int wb200_count_offsets(int n_samples, int n_bins, const int32_t *d_counts, int3
 
 int wb200_throw_photons(const wb200_photon_args *args, void *stream)
 {
-    return throw_photons(args, 0, (cudaStream_t)stream);
+    return throw_photons(args, 0, (cudaStream_t)stream, nullptr);
 }
 
 // Batches of an exposure carry the global index of their first sub-sample so
 // Philox counters do not depend on the batching.
 int wb200_throw_photons_at(const wb200_photon_args *args, int sample0, void *stream)
 {
-    return throw_photons(args, sample0, (cudaStream_t)stream);
+    return throw_photons(args, sample0, (cudaStream_t)stream, nullptr);
 }
 
 int wb200_throw_photons_direct(const wb200_photon_args *args, const wb200_gather_args *g,
@@ -333,55 +398,7 @@ int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels, in
     return WB200_OK;
 }
 
-int wb200_reads(const wb200_reads_args *a, void *stream)
-{
-    WB_REQUIRE(a != nullptr, "null args");
-    WB_REQUIRE(a->n_reads >= 1 && a->n_reads <= 15, "1 <= n_reads <= 15");
-    WB_REQUIRE(a->F > 2 * a->border && (a->F % 2) == 0, "F must be even and > 2*border");
-    WB_REQUIRE(a->d_dt && a->d_acc && a->d_out, "null buffer");
-    WB_REQUIRE(!a->add_sky || a->d_sky || a->d_draw_sky, "sky plane missing");
-    WB_REQUIRE(!a->add_dark || a->d_draw_dark || (a->d_dark && a->d_dark_err), "dark planes missing");
-    if (a->add_nonlinear)
-        for (int i = 0; i < 7; ++i)
-            WB_REQUIRE(a->d_nl[i], "non-linearity planes missing");
-    WB_REQUIRE(!a->d_cos_head || a->n_cosmics == 0 || (a->d_cos_next && a->d_cos_read && a->d_cos_energy),
-               "cosmic lists missing");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t pairs = (size_t)a->F * a->F / 2;
-    const int blocks = (int)((pairs + 255) / 256);
-    if (a->exact_newton && a->add_nonlinear) {
-        WB_REQUIRE(!a->out_f32, "exact_newton needs the float64 output");
-        WB_REQUIRE(a->d_newton_iters, "newton scratch missing");
-        WB_CUDA(cudaMemsetAsync(a->d_newton_iters, 0, sizeof(int32_t) * 16, st));
-        k_reads<1><<<blocks, 256, 0, st>>>(*a);
-        WB_LAUNCHED("k_reads<1>");
-        k_reads<2><<<blocks, 256, 0, st>>>(*a);
-        WB_LAUNCHED("k_reads<2>");
-    } else if (a->fast_math && !a->d_draw_noise && !a->d_draw_sky && !a->d_draw_dark && !a->d_draw_rn &&
-               !getenv("WB200_EXACT_READS") && !getenv("WB200_GENERIC_READS")) {
-        // native mode without host-drawn planes: the throughput kernel (reads_native.cuh)
-        static const size_t smem = RN_SMEM;
-        static const cudaError_t attr64 = cudaFuncSetAttribute(
-            k_reads_native<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        static const cudaError_t attr32 = cudaFuncSetAttribute(
-            k_reads_native<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        WB_CUDA(attr64);
-        WB_CUDA(attr32);
-        const int nblocks = (int)((pairs + RN_THREADS - 1) / RN_THREADS);
-        if (a->out_f32)
-            k_reads_native<true><<<nblocks, RN_THREADS, smem, st>>>(*a);
-        else
-            k_reads_native<false><<<nblocks, RN_THREADS, smem, st>>>(*a);
-        WB_LAUNCHED("k_reads_native");
-    } else {
-        if (a->fast_math && !getenv("WB200_EXACT_READS"))
-            k_reads<0, true><<<blocks, 256, 0, st>>>(*a);
-        else
-            k_reads<0, false><<<blocks, 256, 0, st>>>(*a);
-        WB_LAUNCHED("k_reads<0>");
-    }
-    return WB200_OK;
-}
+int wb200_reads(const wb200_reads_args *args, void *stream) { return launch_reads(args, (cudaStream_t)stream); }
 
 // ---------------------------------------------------------------------------
 // PSF drop-in (wayne/pyparallel_menu.c:10-113): host buffers in, host frame out.
@@ -474,7 +491,7 @@ int wb200_psf_host(const int *counts, int size, const double *x_pos, const doubl
     a.d_normals_base = (int64_t *)(m + 24);
     a.d_normals = d_norm.as<double>();
     a.d_win = d_win.as<int32_t>();
-    rc = throw_photons(&a, 0, st);
+    rc = throw_photons(&a, 0, st, nullptr);
     if (rc)
         return rc;
     WB_CUDA(cudaMemcpyAsync(frame_out, d_win.p, npix * 4, cudaMemcpyDeviceToHost, st));
@@ -578,3 +595,5 @@ int wb200_microbench(int which, int iters, double *ms_out, double *ops_out)
 }
 
 } // extern "C"
+
+#include "context.cuh"

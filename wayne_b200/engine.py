@@ -43,6 +43,11 @@ ZMAX = {_lib.RNG_PHILOX: 8.3, _lib.RNG_RANDR: 6.6}
 WINDOW_BYTES_CAP = 2 << 30          # HBM spent on sub-sample windows per batch
 
 
+def _lib_params_calb():
+    from . import params
+    return params._calb_dir
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -297,6 +302,15 @@ class DeviceEngine(object):
         done.synchronize()
         return arr
 
+    def exposure_context(self, grism, detector, subarray, sampseq):
+        """The resident context of one instrument configuration on this GPU (created once)."""
+        key = ('ctx', grism.name, getattr(grism, 'flat_file_name', None), getattr(grism, 'sky_file_name', None),
+               detector.gain_file_name, detector.non_linear_file_name, int(subarray), sampseq,
+               _lib_params_calb())
+        if key not in self._planes:
+            self._planes[key] = ExposureContext(self, grism, detector, subarray, sampseq)
+        return self._planes[key]
+
     def cached_plane(self, key, make):
         if key not in self._planes:
             self._planes[key] = make()
@@ -329,6 +343,11 @@ class DeviceEngine(object):
             out[name] = (t + a.elapsed_time(b), n + 1)
         if reset:
             self._marks = []
+        for ctx in self._planes.values():          # exposures queued through resident contexts
+            if isinstance(ctx, ExposureContext):
+                for name, (t, n) in ctx.stage_times().items():
+                    t0, n0 = out.get(name, (0.0, 0))
+                    out[name] = (t0 + t, n0 + n)
         return out
 
 
@@ -769,6 +788,13 @@ class ExposureRun(object):
         """Electrons thrown in this exposure (incl. those landing off-frame)."""
         return int(self.d_totals.sum().item())
 
+    def thrown(self):
+        """The same as a 0-d device tensor (no synchronisation)."""
+        return self.d_totals.sum()
+
+    def counts_host(self):
+        return self.d_counts.cpu().numpy()
+
     # ------------------------------------------------------------------
     def reads(self, dt_s, key=(0, 0), sky_rate=0.0, sky_plane=None, gain_plane=None, zero=None,
               dark=None, nl_planes=None, noise=(0.0, 0.0), clip=None, read_noise=0.0,
@@ -856,3 +882,235 @@ class ExposureRun(object):
         self._keep_reads = keep + [d_dt, d_iters]
         self.newton_iters = d_iters
         return out
+
+
+# ---------------------------------------------------------------------------------------
+# Exposure-level interface: one wb200_exposure_run call per exposure
+# ---------------------------------------------------------------------------------------
+def _f32_plane(a):
+    """Host plane in the calibration file's float32, native byte order, contiguous.
+    Every value must survive the round trip (the library checks float64 input itself;
+    this keeps the upload at half the bytes)."""
+    a = np.asarray(a)
+    out = np.ascontiguousarray(a, dtype=np.float32)
+    if a.dtype.itemsize > 4 and not np.array_equal(out.astype(np.float64), np.asarray(a, dtype=np.float64),
+                                                   equal_nan=True):
+        raise ValueError("calibration plane is not float32-representable")
+    return out
+
+
+class ContextRun(object):
+    """What an exposure queued through the context leaves behind for the caller (the
+    counterpart of ExposureRun for tests, the bench and ExposureGenerator.photons)."""
+
+    def __init__(self, ctx, N, W, R, stats):
+        self.ctx, self.N, self.W, self.R = ctx, N, W, R
+        self.stats = stats                 # device int64 [4]: thrown, binned, dropped, 0
+        self.tally = stats[1:3]
+        self.lost = None
+        self.win_geometry = (None, None, ctx.info()[0])
+
+    def thrown(self):
+        return self.stats[0]
+
+    def photons(self):
+        return int(self.stats[0].item())
+
+    def counts_host(self):
+        return self.ctx.read_scratch(0, (self.N, self.W), np.int32)
+
+    def totals_host(self):
+        return self.ctx.read_scratch(1, (self.N,), np.uint64)
+
+    def trace_host(self):
+        return self.ctx.read_scratch(2, (self.N, _lib.TRACE_STRIDE), np.float64)
+
+    def tables_host(self):
+        return tuple(self.ctx.read_scratch(3, (5, self.W), np.float64))
+
+
+class ExposureContext(object):
+    """Python face of a ``wb200_ctx``: the resident planes of one instrument configuration
+    (grism, SUBARRAY, SAMPSEQ) on one GPU and the single call that queues an exposure."""
+
+    def __init__(self, engine, grism, detector, subarray, sampseq):
+        self.e, self.grism, self.det = engine, grism, detector
+        self.S, self.seq = int(subarray), sampseq
+        self.L = 1014 if self.S == 1024 else self.S
+        self.F = min(self.S + 10, 1024)
+        self._h = C.c_void_p()
+        check(lib.wb200_ctx_create(engine.device.index, C.byref(self._h)), "wb200_ctx_create")
+        self._have = set()
+        self._dark_reads = 0
+        self._set_instrument()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.wb200_ctx_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:      # interpreter shutdown
+            pass
+
+    def _check(self, rc, what):
+        if rc != _lib.OK:
+            msg = lib.wb200_ctx_last_error(self._h)
+            raise _lib.WayneB200Error("{} failed ({}): {}".format(
+                what, rc, msg.decode("utf-8", "replace") if msg else ""))
+
+    def _set_instrument(self):
+        g, det = self.grism, self.det
+        sens_wl, sens_val = g._load_sens()
+        fl_n, f32, wmin, wmax = 1014, 1, 0.0, 1.0
+        inst = _lib.Instrument()
+        inst.subarray, inst.L, inst.F, inst.border = self.S, self.L, self.F, BORDER
+        inst.flat_off = g.flat_offset(self.S)
+        inst.flat_n, inst.flat_f32, inst.flat_wmin, inst.flat_wmax = fl_n, f32, wmin, wmax
+        inst.n_sens = len(sens_wl)
+        inst.sub_scale = float(507 - self.S // 2)
+        for i, v in enumerate(np.concatenate([np.asarray(p.coeffs, dtype=np.float64) for p in
+                                              (g.psf_ratio_poly, g.psf_sigmal_poly, g.psf_sigmah_poly)])):
+            inst.psf_poly12[i] = v
+        for i in range(9):
+            inst.trace_coeff9[i] = float(g.trace_coeff[i])
+            inst.wl_sol9[i] = float(g.wl_solution[i])
+        inst.const_gain = float(det.constant_gain)
+        inst.clip_lo, inst.clip_hi = float(det.min_counts), float(det.max_counts)
+        inst.read_noise = float(det.read_noise)
+        self._inst = inst
+        self._check(lib.wb200_ctx_set_instrument(self._h, C.byref(inst)), "wb200_ctx_set_instrument")
+        self._upload(_lib.PLANE_SENS_WL, np.ascontiguousarray(sens_wl, dtype=np.float64), _lib.F64)
+        self._upload(_lib.PLANE_SENS_VAL, np.ascontiguousarray(sens_val, dtype=np.float64), _lib.F64)
+
+    def _upload(self, which, arr, dtype):
+        self._check(lib.wb200_ctx_upload_plane(self._h, which, C.c_void_p(arr.ctypes.data), dtype, arr.size),
+                    "wb200_ctx_upload_plane")
+        self._have.add(which)
+
+    def ensure_planes(self, add_flat, sky, gain, nonlinear, dark_reads, zero_read):
+        """Upload (once) the planes the requested terms read.  dark_reads = number of reads
+        that need dark planes (0: none); zero_read = host array or None."""
+        g, det, e = self.grism, self.det, self.e
+        if add_flat and _lib.PLANE_FLAT0 not in self._have:
+            fl = g._load_flat()
+            inst = self._inst
+            inst.flat_n = int(fl['f'][0].shape[0])
+            inst.flat_f32 = 1 if fl['f'][0].dtype.itemsize == 4 else 0
+            inst.flat_wmin, inst.flat_wmax = float(fl['wmin']), float(fl['wmax'])
+            self._check(lib.wb200_ctx_set_instrument(self._h, C.byref(inst)), "wb200_ctx_set_instrument")
+            for i in range(4):
+                self._upload(_lib.PLANE_FLAT0 + i, _f32_plane(fl['f'][i]), _lib.F32)
+        if sky and _lib.PLANE_SKY not in self._have:
+            self._upload(_lib.PLANE_SKY, _f32_plane(e.bordered(g.get_master_sky(self.L), self.F)), _lib.F32)
+        if gain and _lib.PLANE_GAIN not in self._have:
+            self._upload(_lib.PLANE_GAIN, _f32_plane(e.bordered(det.get_gain(self.S), self.F, fill=1.0)), _lib.F32)
+        if nonlinear and _lib.PLANE_NL0 not in self._have:
+            for i, p in enumerate(det.non_linear_planes(self.F)[:4]):
+                self._upload(_lib.PLANE_NL0 + i, _f32_plane(p), _lib.F32)
+        if dark_reads > self._dark_reads:
+            planes = [det.dark_planes(r + 1, self.S, self.seq) for r in range(1, dark_reads + 1)]
+            self._upload(_lib.PLANE_DARK, _f32_plane(np.stack([p[0] for p in planes])), _lib.F32)
+            self._upload(_lib.PLANE_DARK_ERR, _f32_plane(np.stack([p[1] for p in planes])), _lib.F32)
+            self._dark_reads = dark_reads
+        if zero_read is not None and _lib.PLANE_ZERO not in self._have:
+            self._upload(_lib.PLANE_ZERO, np.ascontiguousarray(zero_read, dtype=np.float64), _lib.F64)
+
+    STAGES = ('k_stage1', 'k_counts', 'k_cosmic_chains', 'k_throw', 'k_reads')
+
+    def profile(self, on):
+        self._check(lib.wb200_ctx_profile(self._h, 1 if on else 0), "wb200_ctx_profile")
+
+    def stage_times(self):
+        """{stage: (total ms, launches)} since the last call (synchronises the device)."""
+        ms, n = (C.c_double * 8)(), (_lib.c_i64 * 8)()
+        self._check(lib.wb200_ctx_stage_times(self._h, ms, n), "wb200_ctx_stage_times")
+        return {name: (ms[i], n[i]) for i, name in enumerate(self.STAGES) if n[i]}
+
+    def info(self):
+        out = (_lib.c_i64 * 8)()
+        self._check(lib.wb200_ctx_info(self._h, out), "wb200_ctx_info")
+        return list(out)
+
+    def read_scratch(self, which, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        self._check(lib.wb200_ctx_read_scratch(self._h, which, C.c_void_p(out.ctypes.data), out.nbytes),
+                    "wb200_ctx_read_scratch")
+        return out
+
+    def run(self, wl_um, flux, depth, depth_col0, xr, yr, dur_ms, dt_s, read_end, scale, key, count_mode,
+            add_flat, sky_rate, add_gain, add_dark, add_nonlinear, clip, add_read_noise, add_zero, noise,
+            cosmics, out_f32):
+        """Queue one exposure on the current stream; returns (reads tensor [R+1][F][F], ContextRun)."""
+        e = self.e
+        W, N, R = len(wl_um), len(xr), len(read_end)
+        a = _lib.ExposureArgs()
+        a.n_samples, a.n_bins, a.n_reads, a.count_mode = N, W, R, count_mode
+        a.add_flat, a.add_sky, a.add_gain = int(bool(add_flat)), int(bool(sky_rate)), int(bool(add_gain))
+        a.add_dark, a.add_nonlinear, a.clip = int(bool(add_dark)), int(bool(add_nonlinear)), int(bool(clip))
+        a.add_read_noise, a.add_zero = int(bool(add_read_noise)), int(bool(add_zero))
+        a.add_noise = int(bool(noise[0] and noise[1]))
+        a.out_f32 = int(bool(out_f32))
+        a.key0, a.key1 = key[0] & 0xffffffff, key[1] & 0xffffffff
+        a.scale = 1.0 if scale is None else float(scale)
+        a.sky_rate = float(sky_rate or 0.0)
+        a.noise_mean, a.noise_std = float(noise[0] or 0.0), float(noise[1] or 0.0)
+        keep = []          # host arrays must stay alive until the call has copied them (it does before returning)
+
+        def host(arr, dtype=np.float64):
+            arr = np.ascontiguousarray(arr, dtype=dtype)
+            keep.append(arr)
+            return C.c_void_p(arr.ctypes.data)
+
+        a.wl, a.xref, a.yref, a.dur_ms = host(wl_um), host(xr), host(yr), host(dur_ms)
+        a.dt_s, a.read_end = host(dt_s), host(read_end, np.int32)
+        if isinstance(flux, torch.Tensor):
+            keep.append(flux)
+            a.d_flux = flux.data_ptr()
+        else:
+            a.flux = host(flux)
+        slot = None
+        if depth is not None:
+            if hasattr(depth, 'row') and hasattr(depth, 'col'):          # lightcurve.SeparableSignal
+                a.sep_row = host(depth.row[:N])
+                a.sep_col = host(depth.col[depth_col0:depth_col0 + W])
+            elif hasattr(depth, 'coef') and hasattr(depth, 'x'):          # lightcurve.ChebyshevSignal
+                a.cheb_order = int(depth.coef.shape[1])
+                a.cheb_x = host(depth.x[depth_col0:depth_col0 + W])
+                coef = depth.coef[:N]
+                if isinstance(coef, torch.Tensor):
+                    coef = coef.contiguous()
+                    keep.append(coef)
+                    a.d_cheb_coef = coef.data_ptr()
+                else:
+                    a.cheb_coef = host(coef)
+            else:
+                if isinstance(depth, torch.Tensor):
+                    if depth.dtype != torch.float64:
+                        raise ValueError("device planet_signal must be float64")
+                    d_depth = e.to_dev(depth)
+                else:
+                    depth = np.asarray(depth)
+                    if depth.dtype != np.float64 or not depth.flags.c_contiguous:
+                        depth = np.ascontiguousarray(depth, dtype=np.float64)
+                    if depth.nbytes >= (8 << 20):
+                        d_depth, slot = e.upload_async(depth)
+                    else:
+                        d_depth = e.to_dev(depth)
+                keep.append(d_depth)
+                a.depth_ld = int(depth.shape[1])
+                a.d_depth = d_depth.data_ptr() + 8 * int(depth_col0)
+        if cosmics is not None and len(cosmics[0]):
+            a.n_cosmics = len(cosmics[0])
+            a.cos_pixel, a.cos_read = host(cosmics[0], np.int32), host(cosmics[1], np.int32)
+            a.cos_energy = host(cosmics[2])
+        stats = e.empty((4,), torch.int64)
+        a.d_stats = stats.data_ptr()
+        out = e.empty((R + 1, self.F, self.F), torch.float32 if out_f32 else torch.float64)
+        self.profile(e.profile)
+        e.mark('exposure', True)
+        self._check(lib.wb200_exposure_run(self._h, C.byref(a), C.c_void_p(out.data_ptr()), e.stream_ptr()),
+                    "wb200_exposure_run")
+        e.mark('exposure', False)
+        if slot is not None:
+            e.release_upload(slot)
+        return out, ContextRun(self, N, W, R, stats)

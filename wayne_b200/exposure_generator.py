@@ -325,8 +325,8 @@ class ExposureGenerator(object):
         flux = np.asarray(getattr(stellar_flux, 'value', stellar_flux), dtype=np.float64)[i0:i1]
         depth = None
         if planet_signal is not None:
-            if hasattr(planet_signal, 'is_cuda') or hasattr(planet_signal, 'coef'):
-                depth = planet_signal          # CUDA tensor, or lightcurve.ChebyshevSignal
+            if hasattr(planet_signal, 'is_cuda') or hasattr(planet_signal, 'coef') or hasattr(planet_signal, 'row'):
+                depth = planet_signal          # CUDA tensor, lightcurve.ChebyshevSignal / SeparableSignal
             else:
                 depth = np.asarray(planet_signal)
             if depth.ndim != 2 or depth.shape[0] < num_samples:
@@ -334,6 +334,7 @@ class ExposureGenerator(object):
             depth = depth[:num_samples]
         aux = {'dt': dt_s}
         native_cosmics = None
+        host_cosmics = None
         if not compat and cosmic_rate is not None:
             # hit list of the whole exposure (cosmic_rays.py:88-139 per read interval),
             # drawn up front so it rides in the exposure's first small upload
@@ -347,10 +348,22 @@ class ExposureGenerator(object):
                 cols.append(g.integers(0, L, n))
             rows, cols = np.concatenate(rows), np.concatenate(cols)
             if len(rows):
-                aux['cos_pix'] = ((rows + BORDER) * F + (cols + BORDER)).astype(np.int32)
-                aux['cos_rd'] = np.concatenate(rd)
-                aux['cos_en'] = np.concatenate(en)
+                host_cosmics = (((rows + BORDER) * F + (cols + BORDER)).astype(np.int32), np.concatenate(rd),
+                                np.concatenate(en))
+                aux['cos_pix'], aux['cos_rd'], aux['cos_en'] = host_cosmics
                 native_cosmics = True
+
+        sky_rate = float(u.value_in(sky_background, u.count / u.s)) if sky_background else 0.0
+        use_noise = bool(noise_mean and noise_std)
+        if not compat and params.use_context and params.direct_accumulation and not exact_newton:
+            return self._scan_through_context(
+                eng, start_time, wl_um[i0:i1], flux, depth, i0, x_ref + s_x_jitter, s_y_refs + s_y_jitter,
+                dur_ms, dt_s, read_index, scale_factor, key, add_stellar_noise, add_flat, sky_rate,
+                add_gain_variations, add_dark, add_non_linear, clip_values_det_limits, add_read_noise,
+                zero_read, (noise_mean, noise_std) if use_noise else (0.0, 0.0), host_cosmics, out_dtype,
+                device_result, read_times_s, zero_read_info, progress_bar)
+        if hasattr(depth, 'row'):
+            depth = depth.to_array()           # the stage-by-stage path takes the dense form
         run = ExposureRun(eng, self.grism, S, wl_um[i0:i1], flux, depth, i0,
                           x_ref + s_x_jitter, s_y_refs + s_y_jitter, dur_ms, scale_factor,
                           np.asarray(read_index, dtype=np.int32), aux=aux)
@@ -374,9 +387,6 @@ class ExposureGenerator(object):
                               "Off".format(self.SAMPSEQ, S), WFC3SimNoDarkFileWarning)
                 self.exposure.exp_info['add_dark'] = False
                 add_dark = False
-
-        sky_rate = float(u.value_in(sky_background, u.count / u.s)) if sky_background else 0.0
-        use_noise = bool(noise_mean and noise_std)
 
         if compat:
             # the reference's numpy stream, in its order
@@ -450,19 +460,56 @@ class ExposureGenerator(object):
             out_f32=(np.dtype(out_dtype) == np.float32), const_gain=det.constant_gain,
             fast_math=not compat)
 
+        return self._hand_over(eng, out, run.lost, device_result, start_time, read_times_s, zero_read_info,
+                               num_samples, progress_bar)
+
+    def _scan_through_context(self, eng, start_time, wl_um, flux, depth, depth_col0, xr, yr, dur_ms, dt_s,
+                              read_index, scale_factor, key, add_stellar_noise, add_flat, sky_rate,
+                              add_gain_variations, add_dark, add_non_linear, clip, add_read_noise, zero_read,
+                              noise, cosmics, out_dtype, device_result, read_times_s, zero_read_info,
+                              progress_bar):
+        """Native mode: the whole exposure is ONE call on the configuration's resident context
+        (include/wayne_b200.h, wb200_exposure_run) -- stage 1, counts, thrower + flat, ramp pass."""
+        from . import _lib
+        det, S = self.detector, self.SUBARRAY
+        R = len(read_index)
+        ctx = eng.exposure_context(self.grism, det, S, self.SAMPSEQ)
+        if add_dark:
+            try:
+                ctx.ensure_planes(False, False, False, False, R, None)
+            except WFC3SimNoDarkFileError:
+                warnings.warn("No Dark file found for SAMPSEQ = {}, SUBARRAY={} - Switching Dark "
+                              "Off".format(self.SAMPSEQ, S), WFC3SimNoDarkFileWarning)
+                self.exposure.exp_info['add_dark'] = False
+                add_dark = False
+        ctx.ensure_planes(add_flat, bool(sky_rate), add_gain_variations, add_non_linear, 0, zero_read)
+        out, run = ctx.run(wl_um, flux, depth, depth_col0, xr, yr, dur_ms, dt_s,
+                           np.asarray(read_index, dtype=np.int32), scale_factor, key,
+                           _lib.COUNT_POISSON if add_stellar_noise else _lib.COUNT_ROUND,
+                           add_flat, sky_rate, add_gain_variations, add_dark, add_non_linear, clip,
+                           add_read_noise, zero_read is not None, noise, cosmics,
+                           np.dtype(out_dtype) == np.float32)
+        self._run = run
+        return self._hand_over(eng, out, None, device_result, start_time, read_times_s, zero_read_info,
+                               len(xr), progress_bar)
+
+    def _hand_over(self, eng, out, lost, device_result, start_time, read_times_s, zero_read_info,
+                   num_samples, progress_bar):
+        """Leave the reads in HBM (device_result) or queue the single device->host copy into
+        pooled pinned memory; exposure.reads waits for it on first access."""
+        from . import _lib
+        R = len(read_times_s)
         if device_result:
             eng.retire()
             self.exposure.device_reads = out
             self.exp_info['sim_time'] = (time.time() - start_time) * u.s
             return self.exposure
-        # the single device -> host copy, queued on the copy stream into pooled
-        # pinned memory; exposure.reads waits for it on first access
-        done, reads_host, lost = eng.fetch_async(out, small=run.lost)
+        done, reads_host, lost = eng.fetch_async(out, small=lost)
         nsamp = self.NSAMP
 
         def materialize(exp):
             done.synchronize()
-            n_lost = int(lost[0])
+            n_lost = int(lost[0]) if lost is not None else 0
             if n_lost:
                 raise _lib.WayneB200Error(
                     "{} electrons fell outside their sub-sample window".format(n_lost))

@@ -233,6 +233,32 @@ class ChebyshevSignal(object):
         return np.polynomial.chebyshev.chebval(self.x, self._host_coef().T)
 
 
+class SeparableSignal(object):
+    """Planet signal of an exposure that factorises: depth[s][w] = lightcurve[s] * depth[w]
+    (one light-curve shape times a depth spectrum -- what a caller builds with
+    ``depth[None, :] * lightcurve[:, None]`` before handing it to scanning_frame).  Passed
+    as this object, the two factors are uploaded (8 (N + W) bytes instead of 8 N W: 65 KB
+    instead of 135 MB for a 4116 x 4096 exposure) and the counts kernel forms the very same
+    double product per cell, so the exposure is bit-identical to the dense array's."""
+
+    ndim = 2
+
+    def __init__(self, lightcurve, depth):
+        self.row = np.ascontiguousarray(lightcurve, dtype=np.float64)
+        self.col = np.ascontiguousarray(depth, dtype=np.float64)
+        if self.row.ndim != 1 or self.col.ndim != 1:
+            raise ValueError("lightcurve [n_samples] and depth [n_wl] must be one-dimensional")
+        self.shape = (self.row.shape[0], self.col.shape[0])
+
+    def __getitem__(self, item):
+        if isinstance(item, slice):
+            return SeparableSignal(self.row[item], self.col)
+        return self.col * self.row[item]
+
+    def to_array(self):
+        return self.col[None, :] * self.row[:, None]
+
+
 def planet_signal(t, depth_spectrum, ldcoeffs, period, a, e, inc_deg, w_deg, t0, order=8, nodes=96,
                   rp_body=None):
     """ChebyshevSignal of the reference's planet signal for sample times t [days]

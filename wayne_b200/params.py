@@ -26,6 +26,12 @@ rng = os.environ.get("WAYNE_B200_RNG", "philox")
 direct_accumulation = os.environ.get("WAYNE_B200_DIRECT", "1") != "0"
 
 
+# native mode: one wb200_exposure_run call per exposure on a resident context
+# (include/wayne_b200.h, "Exposure-level interface").  Off = the stage-by-stage calls driven
+# from Python (engine.ExposureRun), kept as the A/B reference and used by the parity mode.
+use_context = os.environ.get("WAYNE_B200_CONTEXT", "1") != "0"
+
+
 def set_calibration_dir(path):
     """Point the package at a calibration directory (affects objects built afterwards)."""
     global _calb_dir
