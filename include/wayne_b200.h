@@ -439,6 +439,11 @@ typedef struct wb200_exposure_args {
     const double *cheb_coef;    /* HOST [N][cheb_order], or NULL when d_cheb_coef    */
     const double *sep_row;      /* separable planet signal (see wb200_counts_args):  */
     const double *sep_col;      /* HOST [N] and [W]; both NULL otherwise             */
+    const double *depth;        /* HOST dense planet signal [N][depth_ld] (first used */
+                                /* column), or NULL: uploaded by the library on its   */
+                                /* upload stream, right behind the small arrays, into */
+                                /* a ring of device buffers (pinned memory makes the  */
+                                /* copy asynchronous; pageable memory works, slower)  */
     const int32_t *cos_pixel;   /* [n_cosmics] bordered flat pixel index             */
     const int32_t *cos_read;    /* [n_cosmics] read interval                         */
     const double *cos_energy;   /* [n_cosmics] electrons                             */

@@ -52,8 +52,11 @@ def flat_value(cal, grism_name, subarray, x_ref, y_ref, rows, cols):
 
 def expected_interval_images(counts, x_pos, y_pos, ratio, sigl, sigh, read_index, L, cal=None,
                              grism_name='G141', subarray=1024, refs=None, batch=16, device=None,
-                             zmax=8.5):
+                             zmax=8.5, with_var=False):
     """E[R][L][L] (float64 numpy): expected electrons per read interval and pixel.
+    with_var: also the exact variance V[R][L][L] -- the electrons of a bin are multinomial over
+    the pixels, so Var = sum n p (1 - p) (flat^2-weighted), a few per cent below E in the
+    trace's core where one pixel takes a sizeable share of a bin.
 
     counts [N][W] int; x_pos, y_pos [N][W] frame coordinates of the bins (already
     minus sub_scale); ratio, sigl, sigh [W]; read_index = last sub-sample of each
@@ -63,6 +66,7 @@ def expected_interval_images(counts, x_pos, y_pos, ratio, sigl, sigh, read_index
     N, W = counts.shape
     R = len(read_index)
     out = torch.zeros((R, L, L), dtype=torch.float64, device=dev)
+    var = torch.zeros((R, L, L), dtype=torch.float64, device=dev) if with_var else None
     cnt = torch.as_tensor(np.ascontiguousarray(counts), device=dev).to(torch.float64)
     nh = torch.floor(cnt * torch.as_tensor(ratio, device=dev)[None, :])      # (int)(counts*ratio), counts >= 0
     nh = torch.minimum(torch.clamp(nh, min=0.0), cnt)
@@ -93,12 +97,15 @@ def expected_interval_images(counts, x_pos, y_pos, ratio, sigl, sigh, read_index
                 px = _cdf_diff(x_lo, x_hi - x_lo, xs[sl_b], sig)             # [B][W][NX]
                 py = _cdf_diff(y_lo, y_hi - y_lo, ys[sl_b], sig)             # [B][W][NY]
                 img = torch.bmm((py * n_e[:, :, None]).transpose(1, 2), px)  # [B][NY][NX]
+                img2 = torch.bmm((py * py * n_e[:, :, None]).transpose(1, 2), px * px) if with_var else None
                 # frame test 0 < x < nr, 0 < y < nc (pyparallel_menu.c:93): clip the box
                 cx0, cx1 = max(x_lo, 1), min(x_hi, L)
                 cy0, cy1 = max(y_lo, 1), min(y_hi, L)
                 if cx0 >= cx1 or cy0 >= cy1:
                     continue
                 img = img[:, cy0 - y_lo:cy1 - y_lo, cx0 - x_lo:cx1 - x_lo]
+                if with_var:
+                    img2 = img2[:, cy0 - y_lo:cy1 - y_lo, cx0 - x_lo:cx1 - x_lo]
                 if cal is not None:
                     rows = torch.arange(cy0, cy1, device=dev)
                     cols = torch.arange(cx0, cx1, device=dev)
@@ -117,7 +124,14 @@ def expected_interval_images(counts, x_pos, y_pos, ratio, sigl, sigh, read_index
                         cal['flat_wmax'] - cal['flat_wmin'])
                     f = [p[Y][:, X][None] for p in flat_planes]
                     val = f[0] + f[1] * w + f[2] * w * w + f[3] * w * w * w
-                    img = img * val.to(torch.float32).to(torch.float64)
+                    val = val.to(torch.float32).to(torch.float64)
+                    if with_var:                       # Var(flat * n) = flat^2 (n p - n p^2)
+                        var[r, cy0:cy1, cx0:cx1] += ((img - img2) * val * val).sum(dim=0)
+                    img = img * val
+                elif with_var:
+                    var[r, cy0:cy1, cx0:cx1] += (img - img2).sum(dim=0)
                 out[r, cy0:cy1, cx0:cx1] += img.sum(dim=0)
         first = last + 1
+    if with_var:
+        return out.cpu().numpy(), var.cpu().numpy()
     return out.cpu().numpy()

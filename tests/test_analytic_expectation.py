@@ -14,9 +14,10 @@ def test_expectation_matches_the_reference_thrower():
     n_seeds = 24
     for seed in range(n_seeds):
         tot += O.psf_port(test=1000 + 37 * seed, threads=1 + seed % 3, **case)
-    exp = analytic.expected_interval_images(
+    exp, var = analytic.expected_interval_images(
         case['counts'][None, :], case['x'][None, :], case['y'][None, :], case['ratio'], case['sigl'],
-        case['sigh'], [0], 256, device='cpu')[0] * n_seeds
+        case['sigh'], [0], 256, device='cpu', with_var=True)
+    exp, var = exp[0] * n_seeds, var[0] * n_seeds
     # the reference tests x against nr and y against nc with strict > 0: nothing lands in row / column 0
     assert tot[0].sum() == 0 and tot[:, 0].sum() == 0 and exp[0].sum() == 0 and exp[:, 0].sum() == 0
     assert abs(tot.sum() - exp.sum()) < 5 * np.sqrt(exp.sum())
@@ -24,7 +25,10 @@ def test_expectation_matches_the_reference_thrower():
     z = (tot[m] - exp[m]) / np.sqrt(exp[m])
     assert m.sum() > 3000
     assert abs(z.mean()) < 5 / np.sqrt(m.sum())
-    assert 0.93 < z.std() < 1.05        # multinomial: slightly below 1
+    assert 0.93 < z.std() < 1.05        # multinomial: slightly below 1 ...
+    zv = (tot[m] - exp[m]) / np.sqrt(var[m])
+    assert 0.97 < zv.std() < 1.03       # ... and 1 against the exact multinomial variance
+    assert np.all(var <= exp + 1e-9) and var[m].min() > 0
     assert np.abs(z).max() < 6.0
     # the far halo (expectation below one electron per pixel) holds what it should in total
     halo = exp < 1.0

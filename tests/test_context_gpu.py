@@ -34,7 +34,8 @@ def test_single_call_equals_staged_path_bit_for_bit(calb_dir, monkeypatch):
     from wayne import units as u
     from wayne.trend_generators.scan_speed_varations import SSVSine
     wl, flux, planet = harness.spectrum(level=3.0e-14)
-    n = 224
+    n = len(_gen()._gen_scanning_sample_times(100 * u.ms)[3]) and \
+        len(np.asarray(u.value_in(_gen()._gen_scanning_sample_times(100 * u.ms)[1], u.ms)))
     depth = np.tile(planet, (n, 1)) * np.linspace(0.1, 1.0, n)[:, None]
     kw = dict(x_ref=404.5, y_ref=457.4, x_jitter=0.02, y_jitter=0.02, wl=wl * u.micron, stellar_flux=flux,
               planet_signal=depth, scan_speed=7.4325 * u.pixel / u.s, sample_rate=100 * u.ms,

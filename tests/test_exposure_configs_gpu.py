@@ -206,7 +206,7 @@ def test_ssv_modulated_sine_exposure(calb_dir):
     np.random.seed(77)
     dur, ri = SSVModulatedSine(10, 1.1, 100).get_subsample_exposure_times(None, None, eg.read_times, rate * u.ms)
     dur = np.asarray(u.value_in(dur, u.ms))
-    assert len(dur) < len(mid) and ri != list(E.gen_scanning_sample_times(rt, rate)[3])
+    assert len(dur) <= len(mid) and ri != list(E.gen_scanning_sample_times(rt, rate)[3])
     dur = np.concatenate([dur, np.zeros(len(mid) - len(dur))])
     rs = np.random.RandomState()
     rs.set_state(np.random.get_state())

@@ -117,7 +117,7 @@ class ExposureArgs(C.Structure):
         ("depth_ld", c_i64),
         ("wl", c_void_p), ("flux", c_void_p), ("xref", c_void_p), ("yref", c_void_p), ("dur_ms", c_void_p),
         ("dt_s", c_void_p), ("read_end", c_void_p), ("cheb_x", c_void_p), ("cheb_coef", c_void_p),
-        ("sep_row", c_void_p), ("sep_col", c_void_p),
+        ("sep_row", c_void_p), ("sep_col", c_void_p), ("depth", c_void_p),
         ("cos_pixel", c_void_p), ("cos_read", c_void_p), ("cos_energy", c_void_p),
         ("d_depth", c_void_p), ("d_cheb_coef", c_void_p), ("d_flux", c_void_p), ("d_stats", c_void_p),
     ]

@@ -81,6 +81,8 @@ struct wb200_ctx {
         char *h = nullptr;
         char *d = nullptr;
         size_t cap = 0;
+        char *big = nullptr; // dense planet signal of the exposure that owns the slot
+        size_t big_cap = 0;
         cudaEvent_t copied = nullptr, done = nullptr;
         bool busy = false;
     } slot[SLOTS];
@@ -296,6 +298,8 @@ int wb200_ctx_destroy(wb200_ctx *c)
             cudaFreeHost(s.h);
         if (s.d)
             cudaFree(s.d);
+        if (s.big)
+            cudaFree(s.big);
         if (s.copied)
             cudaEventDestroy(s.copied);
         if (s.done)
@@ -392,7 +396,9 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     CTX_REQUIRE(c, a->cheb_order >= 0 && a->cheb_order <= 32, "0 <= cheb_order <= 32");
     CTX_REQUIRE(c, !a->cheb_order || (a->cheb_x && (a->cheb_coef || a->d_cheb_coef)), "Chebyshev planet signal incomplete");
     CTX_REQUIRE(c, !a->sep_row == !a->sep_col, "separable planet signal needs both factors");
-    CTX_REQUIRE(c, !(a->sep_row && (a->cheb_order || a->d_depth)), "one form of the planet signal at a time");
+    CTX_REQUIRE(c, !(a->sep_row && (a->cheb_order || a->d_depth || a->depth)) && !(a->depth && (a->d_depth || a->cheb_order)),
+                "one form of the planet signal at a time");
+    CTX_REQUIRE(c, !(a->depth || a->d_depth) || a->depth_ld >= W, "depth_ld must be at least n_bins");
     CTX_REQUIRE(c, a->n_cosmics >= 0 && (a->n_cosmics == 0 || (a->cos_pixel && a->cos_read && a->cos_energy)),
                 "cosmic hit list incomplete");
     const size_t plane = (size_t)F * F;
@@ -474,9 +480,27 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     }
     wb200_ctx::Slot &S = c->slot[c->next_slot];
     c->next_slot = (c->next_slot + 1) % wb200_ctx::SLOTS;
-    if (S.busy)
-        CTX_CUDA(c, cudaEventSynchronize(S.done)); // the exposure that used this slot has finished
+    if (S.busy) {
+        // the pinned staging may be rewritten once the slot's previous copies have run; its device
+        // buffers once the exposure that read them has finished -- the upload stream waits for
+        // that, not the host
+        CTX_CUDA(c, cudaEventSynchronize(S.copied));
+        CTX_CUDA(c, cudaStreamWaitEvent(c->upload, S.done, 0));
+    }
+    const size_t big_bytes = a->depth ? sizeof(double) * ((size_t)(N - 1) * a->depth_ld + W) : 0;
+    if (S.big_cap < big_bytes) {
+        if (S.big) {
+            CTX_CUDA(c, cudaEventSynchronize(S.done));
+            cudaFree(S.big);
+        }
+        S.big = nullptr;
+        S.big_cap = 0;
+        CTX_CUDA(c, cudaMalloc((void **)&S.big, big_bytes));
+        S.big_cap = big_bytes;
+    }
     if (S.cap < total) {
+        if (S.d)
+            CTX_CUDA(c, cudaEventSynchronize(S.done));
         if (S.h)
             cudaFreeHost(S.h);
         if (S.d)
@@ -491,6 +515,8 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     for (const Piece &p : pieces)
         memcpy(S.h + p.off, p.src, p.bytes);
     CTX_CUDA(c, cudaMemcpyAsync(S.d, S.h, total, cudaMemcpyHostToDevice, c->upload));
+    if (a->depth) // same stream, behind the small arrays: one FIFO, nothing overtakes anything
+        CTX_CUDA(c, cudaMemcpyAsync(S.big, a->depth, big_bytes, cudaMemcpyHostToDevice, c->upload));
     CTX_CUDA(c, cudaEventRecord(S.copied, c->upload));
     CTX_CUDA(c, cudaStreamWaitEvent(st, S.copied, 0));
     S.busy = true;
@@ -521,7 +547,7 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     ca.scale = a->scale;
     ca.depth_ld = a->depth_ld;
     ca.d_flux = d_flux;
-    ca.d_depth = a->cheb_order ? nullptr : a->d_depth;
+    ca.d_depth = a->cheb_order ? nullptr : (a->depth ? (const double *)S.big : a->d_depth);
     if (a->sep_row) {
         ca.d_depth = (const double *)dev(i_sc);
         ca.d_sep_row = (const double *)dev(i_sr);
@@ -620,7 +646,7 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     ra.sky_f32 = 1;
     ra.fast_math = 1;
     ra.acc_fixed = 1;
-    ra.zero_acc = 1;
+    ra.zero_acc = getenv("WB200_CTX_MEMSET_ACC") ? 0 : 1; // A/B switch: memset pass instead of the write-back
     ra.planes_f32 = 1;
     ra.const_gain = I.const_gain;
     ra.clip_lo = I.clip_lo;
@@ -648,6 +674,8 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     mark_begin(c, 4, st);
     const int rc = launch_reads(&ra, st);
     mark_end(c, st);
+    if (rc == WB200_OK && !ra.zero_acc)
+        cudaMemsetAsync(c->acc.d, 0, sizeof(long long) * (size_t)R * plane, st);
     if (rc != WB200_OK) {
         // the interval planes may hold this exposure's electrons: restore the "zero between exposures" invariant
         cudaMemsetAsync(c->acc.d, 0, sizeof(long long) * (size_t)R * plane, st);

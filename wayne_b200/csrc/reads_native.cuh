@@ -295,8 +295,6 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
             longlong2 *q = reinterpret_cast<longlong2 *>(
                 reinterpret_cast<long long *>(const_cast<void *>(a.d_acc)) + off);
             nq = *q;
-            if (a.zero_acc) // the interval planes are left zeroed for the next exposure (no memset pass)
-                *q = make_longlong2(0, 0);
         } else
             nacc = ld_stream2(reinterpret_cast<const double *>(a.d_acc) + off);
         if (dark_on) {
@@ -312,6 +310,12 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
         if (acc_fixed) {
             acc[0] = ll2d_fast(nq.x) * (1.0 / 16777216.0);
             acc[1] = ll2d_fast(nq.y) * (1.0 / 16777216.0);
+            // the interval planes are left zeroed for the next exposure (no memset pass).  The store
+            // comes HERE, once this read's load has been consumed: right behind the load it would
+            // have to wait for the load's data (same address) and stall the software pipeline.
+            if (a.zero_acc)
+                *reinterpret_cast<longlong2 *>(reinterpret_cast<long long *>(const_cast<void *>(a.d_acc)) +
+                                               (size_t)r * plane + p) = make_longlong2(0, 0);
         } else {
             acc[0] = nacc.x;
             acc[1] = nacc.y;

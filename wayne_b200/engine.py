@@ -1092,13 +1092,16 @@ class ExposureContext(object):
                     depth = np.asarray(depth)
                     if depth.dtype != np.float64 or not depth.flags.c_contiguous:
                         depth = np.ascontiguousarray(depth, dtype=np.float64)
-                    if depth.nbytes >= (8 << 20):
-                        d_depth, slot = e.upload_async(depth)
-                    else:
-                        d_depth = e.to_dev(depth)
-                keep.append(d_depth)
-                a.depth_ld = int(depth.shape[1])
-                a.d_depth = d_depth.data_ptr() + 8 * int(depth_col0)
+                    # host array: the library uploads it on its own upload stream, behind this
+                    # exposure's small arrays (a pinned array makes that copy asynchronous)
+                    keep.append(depth)
+                    a.depth_ld = int(depth.shape[1])
+                    a.depth = C.c_void_p(depth.ctypes.data + 8 * int(depth_col0))
+                    d_depth = None
+                if d_depth is not None:
+                    keep.append(d_depth)
+                    a.depth_ld = int(depth.shape[1])
+                    a.d_depth = d_depth.data_ptr() + 8 * int(depth_col0)
         if cosmics is not None and len(cosmics[0]):
             a.n_cosmics = len(cosmics[0])
             a.cos_pixel, a.cos_read = host(cosmics[0], np.int32), host(cosmics[1], np.int32)
