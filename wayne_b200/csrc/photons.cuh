@@ -628,15 +628,149 @@ __device__ __forceinline__ void deposit(const wb200_gather_args &ga, const Direc
 #ifndef WB_THROW_MIN_BLOCKS
 #define WB_THROW_MIN_BLOCKS 5
 #endif
+
+// (float)(2^23 + 16-bit field) with the bias word in a REGISTER and the selector an immediate: as
+// written by __byte_perm the selector travels in a register, and ptxas made a fresh copy of it for
+// each of the eight extractions of a trip
+__device__ __forceinline__ float hi16_biased_r(uint32_t w, uint32_t bias)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(w), "r"(bias));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float lo16_biased_r(uint32_t w, uint32_t bias)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7610;" : "=r"(r) : "r"(w), "r"(bias));
+    return __uint_as_float(r);
+}
+
+// `cell` if |px| < hx and |py| < hy, else `other`: two chained compares on the coordinates
+// themselves and ONE select (the compiler's own lowering of the && selects once per axis)
+__device__ __forceinline__ uint32_t select_in_box(float px, float hx, float py, float hy, uint32_t cell,
+                                                  uint32_t other)
+{
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 ax, ay;\n\tabs.ftz.f32 ax, %1;\n\tabs.ftz.f32 ay, %3;\n\t"
+        "setp.lt.ftz.f32 p, ax, %2;\n\tsetp.lt.and.ftz.f32 p, ay, %4, p;\n\tselp.b32 %0, %5, %6, p;\n\t}"
+        : "=r"(r)
+        : "f"(px), "f"(hx), "f"(py), "f"(hy), "r"(cell), "r"(other));
+    return r;
+}
+
+// CTA-uniform values of the native thrower that only the rare paths read: shared memory
+struct ThrowShared {
+    DirectSample ds;
+    int hx, hy, ax0, ay0, wox, woy, s_local, pad;
+    unsigned tally[2]; // slow-path electrons binned inside the frame / dropped outside it
+    uint32_t bias;     // 0x4B000000, read back from here so that it lives in a REGISTER (see hi16_biased_r)
+    uint32_t pad2;
+    wb200_gather_args ga;  // copies of the kernel parameters for the replay (a separate function:
+    wb200_photon_args a;   // parameters taken by reference would be spilled to the stack)
+};
+
+// The electrons of one lane's run of units.
+//   REPLAY = false  the hot loop: every electron of every unit is positioned; one inside the
+//                   accepted part of the tile (fast float test) increments its cell, one outside it
+//                   the warp's spare word `dump`, one that does not exist the word after it.
+//                   No branch depends on where an electron went.
+//   REPLAY = true   run again by a warp that found its spare word non-zero (an electron in ~4e6
+//                   leaves a tile that is clear of the frame's edges): the same units, the same
+//                   arithmetic, and now ONLY the electrons that failed the fast test are looked
+//                   at -- frame test of the reference (pyparallel_menu.c:93), then straight to HBM.
+template <int TW, int TH, bool DIRECT, bool REPLAY>
+__device__ __forceinline__ void throw_run(const BinPar *pb, int j, int n, uint32_t cwk, uint32_t cellk,
+                                          uint32_t dump, float hxf, float hyf, ThrowShared &sh)
+{
+    constexpr int ROW_SHIFT = (TW == 64 ? 8 : TW == 128 ? 9 : TW == 256 ? 10 : 11);
+    static_assert((4 * TW) == (1 << ROW_SHIFT), "ROW_SHIFT = log2(4 TW)");
+    const uint32_t bias = sh.bias; // (a value ptxas cannot see: it would make it the immediate again)
+    int units_cur = 0x7fffffff; // units of the bin pb points at (known after the first load)
+    do {
+        // step to the next staged bin when this one is used up, then (re)load the bin:
+        // branch-free -- at four electrons per unit some lane steps on most trips
+        const bool adv = j >= units_cur;
+        pb += adv ? 1 : 0;
+        j = adv ? 0 : j;
+        const BinPar cur = *pb;
+        units_cur = (cur.nlx + 3) >> 2;
+        const uint32_t r1x = cur.r1x, r1y = cur.r1y;
+        uint32_t pjl, pjh;
+        mul_wide((uint32_t)j, WB_PHILOX_M0, pjl, pjh);
+        const uint4 r = philox4x32_rounds2to10_fixed(make_uint4(r1x, r1y, pjh ^ cwk, pjl));
+        // the unit's width and how many of its four electrons exist
+        const int j4 = 4 * j;
+        const bool wide = j4 < cur.nh;
+        const float sg = wide ? cur.sh : cur.sl;
+        const int rem = (wide ? cur.nh : cur.nlx) - j4;
+        // radius uniforms (k + 1/2) 2^-16; fields k < 16 (everything beyond 4.08 sigma, 1e-3 of the
+        // units) are refined with a 32-bit uniform from a second call
+        float u1[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            u1[h] = fmaf(hi16_biased_r(word_of(r, h), bias), 1.52587890625e-05f, -127.99999237060547f);
+        if (min(min(r.x, r.y), min(r.z, r.w)) < WB_TAIL_WORD) {
+            const uint4 t = philox4x32_rounds2to10_fixed(
+                make_uint4(r1x, r1y, pjh ^ cwk ^ (WB_STREAM_PHOTONS ^ WB_STREAM_PHOTON_TAIL), pjl));
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                if (word_of(r, h) < WB_TAIL_WORD)
+                    u1[h] = throw_u1_tail(word_of(r, h), word_of(t, h));
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const uint32_t w = word_of(r, h);
+            const float rs = sqrt_approx(-lg2_approx(u1[h])) * sg;
+            const float th = fmaf(lo16_biased_r(w, bias), 9.58738019107841e-05f, -807.3892822265625f);
+            const float px = fmaf(cos_approx(th), rs, cur.fx);
+            const float py = fmaf(sin_approx(th), rs, cur.fy);
+            // bits(p + 1.5 2^23, rounded down) = 0x4B400000 + floor(p)
+            const uint32_t bx = __float_as_uint(__fadd_rd(px, 12582912.0f));
+            const uint32_t by = __float_as_uint(__fadd_rd(py, 12582912.0f));
+            if (!REPLAY) {
+                uint32_t ad = select_in_box(px, hxf, py, hyf, cellk + (bx << 2) + (by << ROW_SHIFT), dump);
+                if (h > 0)
+                    ad = (rem > h) ? ad : dump + 4;
+                WB_DEV_ASSERT(ad >= dump - (uint32_t)(8 * 8 + TW * TH * 4) && ad <= dump + 4 && (ad & 3) == 0);
+                red_shared_inc(ad);
+            } else {
+                if ((h > 0 && rem <= h) || (fabsf(px) < hxf && fabsf(py) < hyf))
+                    continue; // does not exist / was binned by the hot loop
+                const int xa = (int)(bx - 0x4B400000u) + sh.ax0, ya = (int)(by - 0x4B400000u) + sh.ay0;
+                if (xa > 0 && xa < sh.a.nr && ya > 0 && ya < sh.a.nc) {
+                    if (DIRECT) {
+                        deposit(sh.ga, sh.ds, xa, ya, 1);
+                        atomicAdd(&sh.tally[0], 1u);
+                    } else
+                        to_window(sh.a, sh.s_local, sh.wox, sh.woy, xa, ya);
+                } else if (DIRECT)
+                    atomicAdd(&sh.tally[1], 1u); // dropped like the reference's (pyparallel_menu.c:93)
+            }
+        }
+        ++j;
+    } while (--n > 0);
+}
+
+template <int TW, int TH, bool DIRECT>
+__device__ __noinline__ void throw_replay(const BinPar *pb, int j, int n, uint32_t cwk, float hxf, float hyf,
+                                          ThrowShared &sh)
+{
+    throw_run<TW, TH, DIRECT, true>(pb, j, n, cwk, 0u, 0u, hxf, hyf, sh);
+}
+
 template <int TW, int TH, bool DIRECT>
 __global__ void __launch_bounds__(256, WB_THROW_MIN_BLOCKS)
 k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_args ga)
 {
     const wb200_photon_args &a = p.a;
-    extern __shared__ int tile[]; // TH*TW, then one spare word (electrons outside the accepted range)
+    // TH*TW tile cells, then per warp two spare words: [0] electrons outside the accepted part of
+    // the tile (a non-zero count makes the warp replay its group), [1] electrons that do not exist
+    extern __shared__ int tile[];
     __shared__ float s_red[4][8];
     __shared__ int s_org[2];
     __shared__ __align__(16) BinPar s_bin[8][32];
+    __shared__ ThrowShared sh;
+    __shared__ double s_pos[4]; // x = wl * [0] + [1], y = x * [2] + [3] (frame coordinates of a bin)
 
     const int s_local = blockIdx.y;
     const uint32_t s_glob = (uint32_t)(p.sample0 + s_local);
@@ -649,17 +783,30 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
 
     if (a.d_totals && a.d_totals[s_local] == 0)
         return;
+    if (DIRECT && ga.d_read_end[ga.n_reads - 1] < (int)s_glob)
+        return; // a sub-sample after the last read belongs to no read (exposure_generator.py:361)
 
-    TraceCoef tc = {}; // (read only when the positions come from the trace, but never indeterminate)
-    if (!a.d_xpos)
-        tc = load_trace(a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE);
+    // Bin positions (_SpectrumTrace.wl_to_x / wl_to_y, grism.py:635-669, minus the sub-array shift,
+    // exposure_generator.py:630-632) with the division hoisted out of the per-bin work:
+    //     x = (wl - c_wl) / m_wl - sub = wl (1 / m_wl) - (c_wl / m_wl + sub)
+    //     y = m_t (x + sub - x_ref) + c_t + y_ref - sub = m_t x + (m_t (sub - x_ref) + c_t + y_ref - sub)
+    // two fp64 FMAs per bin (1e-13 px from trace_xy's operation order).
+    if (threadIdx.x == 0 && !a.d_xpos) {
+        const TraceCoef tc = load_trace(a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE);
+        s_pos[0] = 1.0 / tc.m_wl;
+        s_pos[1] = -(tc.c_wl / tc.m_wl + a.sub_scale);
+        s_pos[2] = tc.m_t;
+        s_pos[3] = tc.m_t * (a.sub_scale - tc.x_ref) + tc.c_t + tc.y_ref - a.sub_scale;
+    }
+    __syncthreads();
     const size_t row = (size_t)s_local * W;
     auto bin_xy = [&](int w, double &x, double &y) {
         if (a.d_xpos) {
             x = a.d_xpos[row + w];
             y = a.d_ypos[row + w];
         } else {
-            trace_xy(tc, a.d_wl[w], a.sub_scale, x, y);
+            x = fma(a.d_wl[w], s_pos[0], s_pos[1]);
+            y = fma(x, s_pos[2], s_pos[3]);
         }
     };
 
@@ -687,7 +834,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         s_red[2][warp] = ymin;
         s_red[3][warp] = ymax;
     }
-    for (int i = threadIdx.x; i < TW * TH; i += blockDim.x)
+    for (int i = threadIdx.x; i < TW * TH + 16; i += blockDim.x)
         tile[i] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -707,50 +854,66 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     }
     __syncthreads();
     const int tx0 = s_org[0], ty0 = s_org[1];
-    // accepted tile-relative range [lo, lo+n): frame test 0 < x < nr, 0 < y < nc
+    // accepted tile-relative range [lo, lo+n): frame test 0 < x < nr, 0 < y < nc ...
     const int lox = max(0, 1 - tx0), loy = max(0, 1 - ty0);
-    const unsigned nx = (unsigned)max(0, min(TW, a.nr - tx0) - lox);
-    const unsigned ny = (unsigned)max(0, min(TH, a.nc - ty0) - loy);
-    int wox = 0, woy = 0;
+    // ... trimmed to an even size and CENTRED: with hx = n/2 the fast test of an electron at
+    // centred coordinate p is |p| < hx -- one float compare per axis on the coordinate itself --
+    // and everything that fails it (the trimmed last column included) takes the exact slow path
+    const int hx = max(0, min(TW, a.nr - tx0) - lox) >> 1, hy = max(0, min(TH, a.nc - ty0) - loy) >> 1;
+    // Bin positions are staged relative to the CENTRE of the accepted range, frame pixel
+    // (ax0, ay0).  floor() of a centred coordinate p comes from the round-down magic add:
+    // bits(p + 1.5 2^23) = 0x4B400000 + floor(p), and the tile cell of (floor px, floor py) is
+    //     tile + ((fy + loy + hy) TW + fx + lox + hx) 4  =  cellk + (bits_x << 2) + (bits_y << log2(4 TW))
+    // with every constant (the two magic offsets too: shifts and adds wrap mod 2^32) folded into
+    // cellk -- no subtraction, no separate address arithmetic per electron.
+    static_assert((TW & (TW - 1)) == 0, "TW must be a power of two");
+    constexpr int ROW_SHIFT = (TW == 64 ? 8 : TW == 128 ? 9 : TW == 256 ? 10 : 11);
+    const int ax0 = tx0 + lox + hx, ay0 = ty0 + loy + hy;
+    const float hxf = (float)hx, hyf = (float)hy;
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t cellk = pin_reg(tile_s + (uint32_t)(((loy + hy) * TW + lox + hx) * 4) - (0x4B400000u << 2) -
+                                   (0x4B400000u << ROW_SHIFT));
+    const uint32_t dump = pin_reg(tile_s + (uint32_t)(TW * TH * 4 + warp * 8));
+    int *const mydump = tile + TW * TH + warp * 2;
     // the sub-sample's flat-field / accumulation constants are CTA-uniform and only used by
     // the flush and by electrons that leave the tile: shared memory, not registers
-    __shared__ DirectSample s_ds;
-    __shared__ unsigned long long s_tally[2]; // electrons binned inside the frame / dropped outside it
-    DirectSample &ds = s_ds;
-    if (DIRECT && ga.d_read_end[ga.n_reads - 1] < (int)s_glob)
-        return; // a sub-sample after the last read belongs to no read (exposure_generator.py:361)
-    if (threadIdx.x == 0)
-        s_tally[0] = s_tally[1] = 0ull;
-    if (DIRECT && threadIdx.x == 0) {
-        const double *t = a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE;
-        ds.g.ox = ds.g.oy = ds.g.s = ds.g.pad = 0;
-        ds.g.x_ref = t[0];
-        ds.g.y_ref = t[1];
-        ds.g.a_t_i = 1 / t[2];
-        ds.g.den = 1.0 / sqrt(ds.g.a_t_i * ds.g.a_t_i + 1);
-        ds.g.m_w = t[4];
-        ds.g.c_w = t[5];
-        ds.inv_range = 1.0 / (ga.flat_wmax - ga.flat_wmin);
-        int r = 0; // read interval of this sub-sample: first r with read_end[r] >= s
-        while (r + 1 < ga.n_reads && ga.d_read_end[r] < (int)s_glob)
-            ++r;
-        ds.acc = reinterpret_cast<long long *>(ga.d_acc) + (size_t)r * ga.F * ga.F;
-    }
-    if (!DIRECT) {
-        wox = a.d_win_ox[s_local];
-        woy = a.d_win_oy[s_local];
+    if (threadIdx.x == 0) {
+        sh.hx = hx;
+        sh.hy = hy;
+        sh.ax0 = ax0;
+        sh.ay0 = ay0;
+        sh.wox = sh.woy = 0;
+        sh.s_local = s_local;
+        sh.tally[0] = sh.tally[1] = 0u;
+        sh.bias = 0x4B000000u;
+        sh.ga = ga;
+        sh.a = a;
+        if (!DIRECT) {
+            sh.wox = a.d_win_ox[s_local];
+            sh.woy = a.d_win_oy[s_local];
+        } else {
+            const double *t = a.d_trace + (size_t)s_local * WB200_TRACE_STRIDE;
+            DirectSample &ds = sh.ds;
+            ds.g.ox = ds.g.oy = ds.g.s = ds.g.pad = 0;
+            ds.g.x_ref = t[0];
+            ds.g.y_ref = t[1];
+            ds.g.a_t_i = 1 / t[2];
+            ds.g.den = 1.0 / sqrt(ds.g.a_t_i * ds.g.a_t_i + 1);
+            ds.g.m_w = t[4];
+            ds.g.c_w = t[5];
+            ds.inv_range = 1.0 / (ga.flat_wmax - ga.flat_wmin);
+            int r = 0; // read interval of this sub-sample: first r with read_end[r] >= s
+            while (r + 1 < ga.n_reads && ga.d_read_end[r] < (int)s_glob)
+                ++r;
+            ds.acc = reinterpret_cast<long long *>(ga.d_acc) + (size_t)r * ga.F * ga.F;
+        }
     }
     __shared__ int s_next; // next 32-bin group to hand out (dynamic: counts are ragged)
     if (threadIdx.x == 0)
         s_next = 0;
     __syncthreads();
+    const int wox = sh.wox, woy = sh.woy;
     BinPar *mybins = s_bin[warp];
-    // bin positions are staged relative to the ACCEPTED origin (tx0+lox, ty0+loy),
-    // so one unsigned compare per axis is the whole bounds test, and the tile cell
-    // of accepted (ix, iy) is tile_acc + (iy*TW + ix)*4 in the shared window
-    const int ax0 = tx0 + lox, ay0 = ty0 + loy;
-    const uint32_t tile_acc = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)((loy * TW + lox) * 4);
-    const uint32_t dump = pin_reg((uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(TW * TH * 4));
     // round-1 constants of the thrower's Philox stream (see ThrowKeys)
     const uint32_t cyk = (keys.hy + s_glob) ^ WB_TK0;
     const uint32_t cwk = pin_reg((keys.hw ^ WB_STREAM_PHOTONS) ^ WB_TK1);
@@ -782,7 +945,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                 bp.sh = (float)a.d_sigh[w];
                 // bins that cannot reach the frame throw nothing: NaN / far-away
                 // positions, NaN widths (the reference's INT_MIN path), and widths
-                // beyond 1e5 px (keeps |coordinate| < 2^22 for floor_magic)
+                // beyond 1e5 px (keeps |coordinate| < 2^22 for the magic-add floor)
                 bool bad = !(fabsf(bp.fx) < 3.0e6f) || !(fabsf(bp.fy) < 3.0e6f);
                 if (nh > 0 && !(fabsf(bp.sh) <= 1.0e5f))
                     bad = true;
@@ -790,7 +953,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                     bad = true;
                 if (bad)
                     cnt = 0;
-                bp.sl *= WB_SQRT_2LN2; // see throw_position
+                bp.sl *= WB_SQRT_2LN2; // the radius is sigma' sqrt(-lg2 u1): no multiply in between
                 bp.sh *= WB_SQRT_2LN2;
             } else {
                 cnt = 0;
@@ -804,7 +967,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         bp.r1x ^= cyk;
         const int incl = warp_incl_scan(units);
         const int total = __shfl_sync(FULL, incl, 31);
-        // bins that have units are staged back to back, so the walk below steps with "+1"
+        // bins that have units are staged back to back, so the walk steps with "+1"
         const uint32_t have = __ballot_sync(FULL, units > 0);
         __syncwarp();
         if (units > 0)
@@ -814,7 +977,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             continue;
         // this lane's run of units
         const int K = (total + 31) >> 5;
-        int q = lane * K;
+        const int q = lane * K;
         const int qend = min(q + K, total);
         // first bin of the run: largest b with excl[b] <= q (all lanes search)
         int b = 0;
@@ -825,94 +988,32 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
                 b += step;
         }
         const int excl_b = __shfl_sync(FULL, incl - units, b);
-        if (q >= qend)
-            continue; // (no collectives below)
-        // flat walk over the run (all lanes execute the same body every trip; a
-        // lane steps to its next bin when the current one has no units left)
         const BinPar *pb = mybins + __popc(have & ((1u << b) - 1u));
-        int j = q - excl_b;            // unit index inside the current bin
-        int n = qend - q;              // units of this lane's run still to do
-        int units_cur = 0x7fffffff;    // units of the bin pb points at (known after the first load)
-        do {
-            // step to the next staged bin when this one is used up, then (re)load the bin:
-            // branch-free -- at four electrons per unit some lane steps on most trips
-            const bool adv = j >= units_cur;
-            pb += adv ? 1 : 0;
-            j = adv ? 0 : j;
-            WB_DEV_ASSERT(pb < mybins + 32);
-            const BinPar cur = *pb;
-            units_cur = (cur.nlx + 3) >> 2;
-            const uint32_t r1x = cur.r1x, r1y = cur.r1y;
-            uint32_t pjl, pjh;
-            mul_wide((uint32_t)j, WB_PHILOX_M0, pjl, pjh);
-            const uint4 r = philox4x32_rounds2to10_fixed(make_uint4(r1x, r1y, pjh ^ cwk, pjl));
-            // the unit's width and how many of its four electrons exist
-            const int j4 = 4 * j;
-            const bool wide = j4 < cur.nh;
-            const float sg = wide ? cur.sh : cur.sl;
-            const int rem = (wide ? cur.nh : cur.nlx) - j4;
-            // two pairs of electrons in straight-line code (their MUFU chains interleave).
-            // Branch-free increments: an electron outside the accepted range adds to a spare
-            // shared word (dump, never read), one that does not exist to the next word
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-                const uint32_t wa = word_of(r, 2 * pr), wb2 = word_of(r, 2 * pr + 1);
-                float u1[2] = {throw_u1(wa), throw_u1(wb2)};
-                if (min(wa, wb2) < WB_TAIL_WORD) { // 5e-4 of the pairs: refine the far tail
-                    const uint4 t = philox4x32_rounds2to10_fixed(
-                        make_uint4(r1x, r1y, pjh ^ cwk ^ (WB_STREAM_PHOTONS ^ WB_STREAM_PHOTON_TAIL), pjl));
-                    if (wa < WB_TAIL_WORD)
-                        u1[0] = throw_u1_tail(wa, word_of(t, 2 * pr));
-                    if (wb2 < WB_TAIL_WORD)
-                        u1[1] = throw_u1_tail(wb2, word_of(t, 2 * pr + 1));
-                }
-                int ix[2], iy[2];
-                uint32_t ad[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int h = 2 * pr + e;
-                    float px, py;
-                    throw_position(u1[e], e ? wb2 : wa, sg, cur.fx, cur.fy, px, py);
-                    ix[e] = floor_magic(px);
-                    iy[e] = floor_magic(py);
-                    ad[e] = select_in_range((uint32_t)ix[e], nx, (uint32_t)iy[e], ny,
-                                            tile_acc + (uint32_t)(iy[e] * (TW * 4) + ix[e] * 4), dump);
-                    if (h > 0)
-                        ad[e] = (rem > h) ? ad[e] : dump + 4;
-                    WB_DEV_ASSERT(ad[e] >= dump - (uint32_t)(TW * TH * 4) && ad[e] <= dump + 4 && (ad[e] & 3) == 0);
-                    red_shared_inc(ad[e]);
-                }
-                if (ad[0] == dump || ad[1] == dump) { // rare: electrons that left the tile
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        if (ad[e] != dump)
-                            continue;
-                        const int xa = ix[e] + ax0, ya = iy[e] + ay0;
-                        if (xa > 0 && xa < a.nr && ya > 0 && ya < a.nc) {
-                            if (DIRECT) {
-                                deposit(ga, ds, xa, ya, 1);
-                                atomicAdd(&s_tally[0], 1ull);
-                            } else
-                                to_window(a, s_local, wox, woy, xa, ya);
-                        } else if (DIRECT)
-                            atomicAdd(&s_tally[1], 1ull); // dropped like the reference's (pyparallel_menu.c:93)
-                    }
-                }
-            }
-            ++j;
-        } while (--n > 0);
+        // flat walk over the run (all lanes execute the same body every trip; a lane steps to
+        // its next bin when the current one has no units left)
+        if (q < qend)
+            throw_run<TW, TH, DIRECT, false>(pb, q - excl_b, qend - q, cwk, cellk, dump, hxf, hyf, sh);
+        __syncwarp();
+        if (mydump[0] != 0) { // some electron of the group left the accepted part of the tile
+            __syncwarp();
+            if (lane == 0)
+                mydump[0] = 0;
+            if (q < qend)
+                throw_replay<TW, TH, DIRECT>(pb, q - excl_b, qend - q, cwk, hxf, hyf, sh);
+            __syncwarp();
+        }
     }
     __syncthreads();
 
     // ---- flush the tile ---------------------------------------------------------
-    unsigned binned = 0;
+    unsigned long long binned = 0;
     for (int i = threadIdx.x; i < TW * TH; i += blockDim.x) {
         const int v = tile[i];
         if (v) {
             const int iy = i / TW, ix = i - iy * TW;
             if (DIRECT) {
-                deposit(ga, ds, ix + tx0, iy + ty0, v);
-                binned += (unsigned)v;
+                deposit(ga, sh.ds, ix + tx0, iy + ty0, v);
+                binned += (unsigned long long)(unsigned)v;
             } else {
                 const int wx = ix + tx0 - wox, wy = iy + ty0 - woy;
                 if ((unsigned)wx < (unsigned)a.win_w && (unsigned)wy < (unsigned)a.win_h)
@@ -924,12 +1025,11 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     }
     if (DIRECT && a.d_tally) {
         // electron bookkeeping of the exposure: binned + dropped == thrown, exactly
-        binned = __reduce_add_sync(FULL, binned);
+        binned = warp_sum_u64(binned);
         if (lane == 0 && binned)
-            atomicAdd(&s_tally[0], (unsigned long long)binned);
-        __syncthreads();
-        if (threadIdx.x < 2 && s_tally[threadIdx.x])
-            atomicAdd((unsigned long long *)a.d_tally + threadIdx.x, s_tally[threadIdx.x]);
+            atomicAdd((unsigned long long *)a.d_tally, binned);
+        if (threadIdx.x < 2 && sh.tally[threadIdx.x]) // (complete: every warp passed the barrier before the flush)
+            atomicAdd((unsigned long long *)a.d_tally + threadIdx.x, (unsigned long long)sh.tally[threadIdx.x]);
     }
 }
 

@@ -85,7 +85,7 @@ int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, cons
         const ThrowKeys keys = throw_keys(a->key0, a->key1);
         const int chunks = (a->n_bins + a->chunk_bins - 1) / a->chunk_bins;
         dim3 grid(chunks, a->n_samples);
-        const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int) + 16; // + the spare word
+        const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int) + 64; // + two spare words per warp
         if (direct) {
             k_throw_philox<TILE_W, TILE_H, true><<<grid, 256, smem, st>>>(p, keys, *direct);
         } else {
