@@ -2,7 +2,7 @@
 """bench.py -- exposures/s and photons/s of the exposure-synthesis path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                    [--workload c4|c1|tiny]
+                    [--workload c4|c1|tiny] [--no-cpu] [--no-extras]
 
 A "step" is one full exposure (stages 1-4: trace/dispersion/sensitivity, Philox
 Poisson counts, electron throw + binning, flat-field gather, fused per-pixel
@@ -23,11 +23,21 @@ metric is quoted on: G141 spatial scan, 1024^2 full frame, NSAMP=15 RAPID,
           in the build container, else the C port) + numpy restatement, timed on
           this host on a bounded sample of the same exposure
 
+  e2e.driver_form / e2e.separable_form   the same exposure with the planet signal handed
+          over the way the visit driver does (Chebyshev coefficients) or as its two
+          factors (lightcurve.SeparableSignal): no 135 MB upload
+  multi_visit   BASELINE configs[4]: 8 visits x 128 exposures of this shape, pointing random
+          walk sigma = 0.02 px, partitioned exposure-wise over the ranks through
+          sharding.run_sharded (strong scaling: the batch is fixed), summaries gathered
+  psf_dropin    the PSF() / apply_psf() drop-in at one sub-sample's shape next to the
+          reference's own C kernel and Cython wrapper (rank 0, N = 1)
+
 N > 1 (torchrun): exposures are independent, so every rank runs its own
 exposures (weak scaling, no data-path collective); value = all ranks' exposures
 / max-over-ranks time.
 
---impl reference: the reference's CPU path (oracle/) alone, rank 0 only.
+--impl reference: the reference's CPU path (oracle/) alone, rank 0 only: the first timed
+step is one FULL exposure (every sub-sample), the others bounded samples of it.
 """
 import argparse
 import json
@@ -54,6 +64,16 @@ WORKLOADS = {
     'tiny': dict(grism='G141', sub=256, nsamp=5, seq='SPARS10', scan=7.4325, rate=200.0, W=512,
                  photons=2.0e6, x_ref=404.497, y_ref=457.427, desc='smoke-sized scan'),
 }
+
+
+def bench_config(wk, n_sub, n_bins):
+    """The `config` object of the JSON line: identical keys and values for both arms."""
+    return {'workload': wk['desc'], 'grism': wk['grism'], 'subarray': wk['sub'], 'nsamp': wk['nsamp'],
+            'sampseq': wk['seq'], 'n_subsamples': int(n_sub), 'n_bins': int(n_bins),
+            'photons_per_exposure_target': wk['photons'], 'out_dtype': 'float64',
+            'terms': 'flat+sky+cosmics+gain+dark+non-linearity+clip+read noise, SSVSine, visit trend',
+            'l2': 'no flush: the per-exposure working set (interval planes 117 MB + dark 117 MB + reads 126 MB '
+                  '[+ planet signal 135 MB]) exceeds the 126 MB L2'}
 
 
 def calibration_dir(wk):
@@ -172,10 +192,62 @@ def measured_peaks():
 # ---------------------------------------------------------------------------
 # CPU reference arm (oracle/): bounded sample of the same exposure
 # ---------------------------------------------------------------------------
-def cpu_reference_exposure(wk, inp, n_sub, threads=None):
-    """Time the reference's CPU path on ``n_sub`` evenly spread sub-samples plus
-    ALL read reductions and the post-exposure chain; extrapolate the sub-sample
-    part to the exposure's N sub-samples.  Returns (seconds per exposure, info)."""
+def psf_case_of(wk, inp, electrons=None, seed=3):
+    """PSF() inputs of ONE sub-sample of the workload (oracle-side arithmetic only):
+    counts, x, y, ratio, sigma_l, sigma_h, frame side."""
+    from oracle import exposure_oracle as E
+    from tests import harness
+    from wayne import units as u
+    cal = harness.oracle_calibration(wk['grism'], dark_mode=None)
+    a_, b_ = (E.G141_TRACE, E.G141_WLSOL) if wk['grism'] == 'G141' else (E.G102_TRACE, E.G102_WLSOL)
+    lim = E.WL_LIMITS[wk['grism']]
+    i0, i1 = E.crop_spectrum_ind(lim[0], lim[1], inp['wl'])
+    s_wl = inp['wl'][i0:i1]
+    ratio, sigl, sigh, sens, dwl = E.bin_tables(s_wl, cal['sens_wl_um'], cal['sens_val'])
+    L_ = 1014 if wk['sub'] == 1024 else wk['sub']
+    tr = E.Trace(wk['x_ref'], wk['y_ref'] + 50.0, a_, b_)
+    sub_scale = 507 - wk['sub'] // 2
+    xs, ys = tr.wl_to_x(s_wl) - sub_scale, tr.wl_to_y(s_wl) - sub_scale
+    dur = np.asarray(u.value_in(inp['dur'], u.ms))
+    mean = E.expected_counts(inp['flux'][i0:i1], None, sens, dwl, float(np.median(dur)), None)
+    if electrons is not None:
+        mean = mean * (electrons / mean.sum())
+    cnt = np.random.RandomState(seed).poisson(mean).astype(np.int32)
+    return cnt, xs, ys, ratio, sigl, sigh, L_
+
+
+def time_reference_psf(case, ncpu):
+    """The reference's native kernel alone on one sub-sample's inputs: PSF() through ctypes per
+    OpenMP team size, and apply_psf() through the unmodified Cython wrapper (what the reference
+    pays per sub-sample, pyparallel.pyx:14-38).  Seconds per call."""
+    from oracle import psf as OP
+    cnt, xs, ys, ratio, sigl, sigh, L_ = case
+    out = {'electrons_per_call': int(cnt.sum()), 'frame': int(L_), 'bins': int(len(cnt)), 'psf_s_by_threads': {}}
+    for t in [t for t in (1, 2, 4, 8, 16, 32) if t <= ncpu]:
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            OP.psf_reference(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, t)
+            el = time.perf_counter() - t0
+            best = el if best is None or el < best else best
+        out['psf_s_by_threads'][str(t)] = best
+    pyx = OP.reference_pyparallel()
+    if pyx is not None:
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            pyx.apply_psf(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, 1)
+            el = time.perf_counter() - t0
+            best = el if best is None or el < best else best
+        out['apply_psf_cython_s_1thread'] = best
+    return out
+
+
+def cpu_reference_exposure(wk, inp, n_sub, threads=None, psf_alone=True):
+    """Time the reference's CPU path on ``n_sub`` evenly spread sub-samples (None: ALL of them,
+    a full un-sampled exposure) plus ALL read reductions and the post-exposure chain; a sampled
+    run extrapolates the sub-sample part to the exposure's N sub-samples.
+    Returns (seconds per exposure, info)."""
     from oracle import exposure_oracle as E
     from oracle import psf as OP
     from tests import harness
@@ -186,15 +258,18 @@ def cpu_reference_exposure(wk, inp, n_sub, threads=None):
     dur = np.asarray(u.value_in(inp['dur'], u.ms))
     ri = inp['read_index']
     N = len(mid)
-    # evenly spread sub-samples, at least one per read, each read closed by its last pick
-    picks, new_ri, first = [], [], 0
-    per_read = max(1, n_sub // len(ri))
-    for last in ri:
-        idx = np.unique(np.linspace(first, last, per_read).round().astype(int))
-        picks.extend(idx.tolist())
-        new_ri.append(len(picks) - 1)
-        first = last + 1
-    picks = np.array(picks)
+    if n_sub is None or n_sub >= N:
+        picks, new_ri = np.arange(N), list(ri)
+    else:
+        # evenly spread sub-samples, at least one per read, each read closed by its last pick
+        picks, new_ri, first = [], [], 0
+        per_read = max(1, n_sub // len(ri))
+        for last in ri:
+            idx = np.unique(np.linspace(first, last, per_read).round().astype(int))
+            picks.extend(idx.tolist())
+            new_ri.append(len(picks) - 1)
+            first = last + 1
+        picks = np.array(picks)
     depth = inp['depth0'][None, :] * inp['lightcurve'][picks][:, None]
     ncpu = os.cpu_count() or 1
     if threads is None:
@@ -214,37 +289,9 @@ def cpu_reference_exposure(wk, inp, n_sub, threads=None):
                     best, threads = el, t
         else:
             threads = 1
-    # B1: the reference's native kernel alone on one sub-sample's
-    # inputs -- PSF() through ctypes and apply_psf() through the unmodified Cython wrapper
-    psf_alone = None
-    if kind == 'reference':
-        a_, b_ = (E.G141_TRACE, E.G141_WLSOL) if wk['grism'] == 'G141' else (E.G102_TRACE, E.G102_WLSOL)
-        lim = E.WL_LIMITS[wk['grism']]
-        i0, i1 = E.crop_spectrum_ind(lim[0], lim[1], inp['wl'])
-        s_wl = inp['wl'][i0:i1]
-        ratio, sigl, sigh, sens, dwl = E.bin_tables(s_wl, cal['sens_wl_um'], cal['sens_val'])
-        L_ = 1014 if wk['sub'] == 1024 else wk['sub']
-        tr = E.Trace(wk['x_ref'], wk['y_ref'] + 50.0, a_, b_)
-        sub_scale = 507 - wk['sub'] // 2
-        xs, ys = tr.wl_to_x(s_wl) - sub_scale, tr.wl_to_y(s_wl) - sub_scale
-        cnt = np.random.RandomState(3).poisson(
-            E.expected_counts(inp['flux'][i0:i1], None, sens, dwl, float(np.median(dur)), None)).astype(np.int32)
-        sweep = {}
-        for t in [t for t in (1, 2, 4, 8, 16, 32) if t <= ncpu]:
-            best = None
-            for _ in range(3):
-                t0 = time.perf_counter()
-                OP.psf_reference(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, t)
-                el = time.perf_counter() - t0
-                best = el if best is None or el < best else best
-            sweep[str(t)] = round(cnt.sum() / best / 1e6, 2)
-        psf_alone = {'electrons_per_call': int(cnt.sum()), 'Melectrons_per_s_by_threads': sweep}
-        pyx = OP.reference_pyparallel()
-        if pyx is not None:
-            t0 = time.perf_counter()
-            pyx.apply_psf(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, 1)
-            psf_alone['apply_psf_cython_Melectrons_per_s_1thread'] = round(
-                cnt.sum() / (time.perf_counter() - t0) / 1e6, 2)
+    psf_info = None
+    if kind == 'reference' and psf_alone:
+        psf_info = time_reference_psf(psf_case_of(wk, inp), ncpu)
     kw = frame_kwargs(wk, 0)
     t0 = time.perf_counter()
     o = E.scanning_frame(cal, wk['grism'], wk['sub'], inp['read_times'], inp['wl'], inp['flux'], depth,
@@ -254,15 +301,45 @@ def cpu_reference_exposure(wk, inp, n_sub, threads=None):
                          sample_times=(mid[picks], dur[picks], new_ri))
     wall = time.perf_counter() - t0
     tm = o['timing']
-    per_exposure = tm['subsamples'] * (N / float(len(picks))) + tm['reads'] + tm['post']
-    photons = o['photons'] * (N / float(len(picks)))
-    info = {'kind': kind, 'cores': int(threads),
-            'sample': '%d of %d sub-samples (evenly spread) + all %d read reductions + post-exposure chain, '
-                      'sub-sample time scaled by %d/%d; %.1f s of CPU work' % (
-                          len(picks), N, len(ri), N, len(picks), wall),
+    scale = N / float(len(picks))
+    per_exposure = tm['subsamples'] * scale + tm['reads'] + tm['post']
+    photons = o['photons'] * scale
+    full = len(picks) == N
+    info = {'kind': kind, 'cores': int(threads), 'full': full,
+            'sample': ('all %d sub-samples (a full, un-sampled exposure) + all %d read reductions + '
+                       'post-exposure chain; %.1f s of CPU work' % (N, len(ri), wall)) if full else
+                      ('%d of %d sub-samples (evenly spread) + all %d read reductions + post-exposure chain, '
+                       'sub-sample time scaled by %d/%d; %.1f s of CPU work' % (
+                           len(picks), N, len(ri), N, len(picks), wall)),
             'seconds_per_exposure': per_exposure, 'photons_per_exposure': photons,
-            'psf_alone': psf_alone}
+            'psf_alone': psf_info}
+    if psf_info and 'apply_psf_cython_s_1thread' in psf_info:
+        # what the real reference pays on top: its Cython wrapper's per-element copy loops
+        # (pyparallel.pyx:23-25, 31-34), once per sub-sample
+        extra = psf_info['apply_psf_cython_s_1thread'] - psf_info['psf_s_by_threads']['1']
+        info['seconds_per_exposure_with_cython_wrapper'] = per_exposure + max(0.0, extra) * N
     return per_exposure, info
+
+
+def cpu_baseline_object(val, info):
+    out = {'value': val, 'unit': 'exposures/s', 'cores': info['cores'], 'kind': info['kind'],
+           'sample': info['sample'], 'photons_per_s': info['photons_per_exposure'] * val,
+           'note': 'lower bound on the reference time: numpy restatement without astropy unit algebra, '
+                   'calibration FITS read once instead of per read, PSF() through ctypes'}
+    if info.get('psf_alone'):
+        pa = info['psf_alone']
+        e = pa['electrons_per_call']
+        out['native_kernel_alone'] = {
+            'electrons_per_call': e, 'bins': pa['bins'], 'frame': pa['frame'],
+            'Melectrons_per_s_by_threads': {k: round(e / v / 1e6, 2) for k, v in pa['psf_s_by_threads'].items()},
+            'apply_psf_cython_Melectrons_per_s_1thread': (round(e / pa['apply_psf_cython_s_1thread'] / 1e6, 2)
+                                                          if 'apply_psf_cython_s_1thread' in pa else None)}
+    if 'seconds_per_exposure_with_cython_wrapper' in info:
+        out['with_cython_wrapper'] = {
+            'value': 1.0 / info['seconds_per_exposure_with_cython_wrapper'], 'unit': 'exposures/s',
+            'note': 'the same exposure with apply_psf() (the unmodified Cython wrapper the reference '
+                    'calls per sub-sample) instead of PSF() through ctypes'}
+    return out
 
 
 def run_reference(args, wk):
@@ -271,25 +348,45 @@ def run_reference(args, wk):
         return
     calibration_dir(wk)
     inp = make_inputs(wk)
-    # sub-samples per step: 8 per read interval for short runs, fewer when many steps are asked for, so
-    # that the whole --steps K --warmup W run stays within a few minutes (the line says what was sampled)
-    n_sub = max(2, min(8, 64 // max(1, args.steps))) * len(inp['read_index'])
-    times, info = [], None
+    from wayne import units as u
+    N, W = len(np.asarray(u.value_in(inp['mid'], u.ms))), len(inp['wl'])
+    R = len(inp['read_index'])
+    # The first timed step is one FULL exposure (every sub-sample, ~30 s on this shape); the other
+    # K - 1 steps are bounded samples of it (2-8 sub-samples per read interval, extrapolated), so that
+    # the whole --steps K --warmup W run stays within a few minutes.  The line says what was sampled.
+    n_sub = max(2, min(8, 64 // max(1, args.steps))) * R
+    from oracle import psf as OP
+    psf_info = time_reference_psf(psf_case_of(wk, inp), os.cpu_count() or 1) if OP.have_reference() else None
+    times, info, full_info = [], None, None
     for i in range(args.warmup + args.steps):
-        t, info = cpu_reference_exposure(wk, inp, n_sub if i >= args.warmup else len(inp['read_index']),
-                                         threads=info['cores'] if info else None)
-        if i >= args.warmup:
+        timed = i >= args.warmup
+        want_full = timed and i == args.warmup and not args.no_full
+        t, info = cpu_reference_exposure(wk, inp, None if want_full else (n_sub if timed else R),
+                                         threads=info['cores'] if info else None, psf_alone=False)
+        if want_full:
+            full_info = dict(info, seconds=t)
+        if timed:
             times.append(t)
     sec = float(np.mean(times))
     val = 1.0 / sec
+    info['psf_alone'] = psf_info
+    if psf_info and 'apply_psf_cython_s_1thread' in psf_info:
+        info['seconds_per_exposure_with_cython_wrapper'] = sec + max(
+            0.0, psf_info['apply_psf_cython_s_1thread'] - psf_info['psf_s_by_threads']['1']) * N
+    if full_info:
+        info['sample'] = '%d timed step(s): step 1 = %s' % (len(times), full_info['sample'])
+        if len(times) > 1:
+            info['sample'] += ('; steps 2..%d = bounded samples (%d sub-samples each + all read reductions + '
+                               'post-exposure chain, sub-sample time scaled to %d)' % (len(times), n_sub, N))
+        info['photons_per_exposure'] = full_info['photons_per_exposure']
     line = {'impl': 'reference', 'metric': 'exposures_per_s', 'value': val, 'unit': 'exposures/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'photons_per_s': info['photons_per_exposure'] / sec,
-            'config': {'workload': wk['desc'], 'rng': 'numpy+rand_r (reference streams)'},
-            'cpu_baseline': {'value': val, 'unit': 'exposures/s', 'cores': info['cores'],
-                             'kind': info['kind'], 'sample': info['sample'],
-                             'native_kernel_alone': info['psf_alone']},
+            'config': bench_config(wk, N, W), 'rng': 'numpy + rand_r (the reference\'s streams)',
+            'step_seconds': [round(t, 3) for t in times],
+            'full_exposure_seconds': round(full_info['seconds'], 3) if full_info else None,
+            'cpu_baseline': cpu_baseline_object(val, info),
             'e2e': {'value': val, 'unit': 'exposures/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -297,6 +394,127 @@ def run_reference(args, wk):
 # ---------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------
+def copy_ceiling_for(world):
+    """The box's measured copy ceiling for this GPU count (tools/copy_ceiling.py, committed under
+    profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_copy_ceiling.json')) as f:
+            return json.load(f).get(str(world))
+    except Exception:      # noqa: BLE001
+        return None
+
+
+def run_multi_visit(wk, inp, wl_q, local, rank, world, barrier, max_over_ranks, n_visits=8, n_exp=128):
+    """BASELINE configs[4]: n_visits x n_exp exposures of the workload's shape, pointing random walk
+    sigma = 0.02 px per exposure, partitioned exposure-wise over the ranks (sharding.run_sharded; no
+    data-path collective), reads copied to the host, per-exposure summaries gathered.  The reference's
+    counterpart is the serial loop of Observation.run_observation (wayne/observation.py:403-405)."""
+    import torch
+    import torch.distributed as dist
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator
+    from wayne_b200 import sharding
+    from wayne_b200.lightcurve import SeparableSignal
+    total = n_visits * n_exp
+    # per visit: a random walk of the pointing and a transit-like light curve sliding through the visit
+    walk = np.empty((n_visits, n_exp, 2))
+    for v in range(n_visits):
+        g = np.random.default_rng(4242 + v)
+        walk[v] = np.cumsum(0.02 * g.standard_normal((n_exp, 2)), axis=0)
+    nsub = len(inp['lightcurve'])
+    group = dist.new_group(backend='gloo') if world > 1 else None     # host-side metadata only
+
+    def make(i, key):
+        v, k = divmod(i, n_exp)
+        lc = 0.5 * (1 + np.tanh((np.linspace(-1, 1, nsub) + 2.0 * (k / float(n_exp) - 0.5)) * 3))
+        eg = ExposureGenerator(*inp['eg_args'], filename='v%02d_%04d_raw.fits' % (v, k + 1), rng='philox',
+                               device=local)
+        kw = frame_kwargs(wk, i)
+        kw.update(x_ref=wk['x_ref'] + walk[v, k, 0], y_ref=wk['y_ref'] + walk[v, k, 1])
+        exp = eg.scanning_frame(kw.pop('x_ref'), kw.pop('y_ref'), kw.pop('x_jitter'), kw.pop('y_jitter'),
+                                wl_q, inp['flux'], SeparableSignal(lc, inp['depth0']),
+                                kw.pop('scan_speed'), kw.pop('sample_rate'), inp['mid'], inp['dur'],
+                                inp['read_index'], rng_key=(1963 + v, key[1]), **kw)
+        return eg, exp
+
+    def finish(h):
+        eg, exp = h
+        last = exp.reads[-1][0]                      # waits for the device->host copy
+        return {'rank': rank, 'photons': eg.photons, 'last_read_sum': float(last[::64, ::64].sum())}
+
+    # warm-up on a few exposures of the batch, then the whole batch
+    sharding.run_sharded(min(total, 4 * world), make, world, rank, visit_seed=0, group=group, finish=finish,
+                         pipeline_depth=3)
+    barrier()
+    import gc
+    gc.collect()
+    gc.disable()
+    t0 = time.perf_counter()
+    merged = sharding.run_sharded(total, make, world, rank, visit_seed=0, group=group, finish=finish,
+                                  pipeline_depth=3)
+    torch.cuda.synchronize()
+    sec = max_over_ranks(time.perf_counter() - t0)
+    gc.enable()
+    assert sorted(merged) == list(range(total))
+    per_rank = [sum(1 for m in merged.values() if m['rank'] == r) for r in range(world)]
+    return {'config': 'BASELINE configs[4]: %d visits x %d exposures of this workload\'s shape, pointing random '
+                      'walk sigma = 0.02 px, exposure-wise over %d rank(s) through sharding.run_sharded, planet '
+                      'signal per exposure (SeparableSignal), reads float64 to the host, summaries gathered '
+                      '(gloo)' % (n_visits, n_exp, world),
+            'exposures': total, 'seconds': sec, 'value': total / sec, 'unit': 'exposures/s', 'scaling': 'strong',
+            'exposures_per_rank': per_rank,
+            'photons_total': int(sum(m['photons'] for m in merged.values())),
+            'checksum': float(sum(m['last_read_sum'] for m in merged.values()))}
+
+
+def run_psf_dropin(wk, inp):
+    """The PSF() / apply_psf() drop-in (include/wayne_b200.h; wayne/pyparallel.pyx:14-38 ->
+    wayne/pyparallel_menu.c:10-113) timed at one sub-sample's shape with HOST arrays in and out, next
+    to the reference's own C kernel and Cython wrapper on this host; outputs compared bit for bit."""
+    from oracle import psf as OP
+    from wayne_b200 import pyparallel
+    ncpu = os.cpu_count() or 1
+    out = []
+    c1 = WORKLOADS['c1']
+    inp1 = inp if wk is c1 else make_inputs(c1)
+    for tag, w_, i_, electrons in (('configs[0] sub-sample: 4494 bins, 5e5 electrons, 256 x 256', c1, inp1, 5.0e5),
+                                   ('1e7 electrons on 1014 x 1014', WORKLOADS['c4'], inp if wk is WORKLOADS['c4']
+                                    else make_inputs(WORKLOADS['c4']), 1.0e7)):
+        case = psf_case_of(w_, i_, electrons=electrons)
+        cnt, xs, ys, ratio, sigl, sigh, L_ = case
+
+        def best_of(fn, n=7):
+            fn()
+            b = None
+            for _ in range(n):
+                t0 = time.perf_counter()
+                r = fn()
+                el = time.perf_counter() - t0
+                b = el if b is None or el < b else b
+            return b, r
+
+        t_psf, frame = best_of(lambda: pyparallel.psf_frame(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, 2))
+        t_apply, flat = best_of(lambda: pyparallel.apply_psf(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, 2))
+        row = {'case': tag, 'electrons': int(cnt.sum()), 'bins': int(len(cnt)), 'frame': int(L_),
+               'PSF_ms': t_psf * 1e3, 'apply_psf_ms': t_apply * 1e3,
+               'Melectrons_per_s': cnt.sum() / t_psf / 1e6}
+        if OP.have_reference():
+            ref = time_reference_psf(case, ncpu)
+            best_t = min(ref['psf_s_by_threads'].values())
+            row['reference'] = {'PSF_ms_by_threads': {k: v * 1e3 for k, v in ref['psf_s_by_threads'].items()},
+                                'apply_psf_cython_ms_1thread': ref.get('apply_psf_cython_s_1thread', 0) * 1e3 or None}
+            row['speedup_vs_reference_PSF_best_threads'] = best_t / t_psf
+            if ref.get('apply_psf_cython_s_1thread'):
+                row['speedup_vs_reference_apply_psf'] = ref['apply_psf_cython_s_1thread'] / t_apply
+            want = OP.psf_reference(cnt, xs, ys, ratio, sigl, sigh, L_, L_, 7, 2)
+            row['bit_exact_vs_reference'] = bool(np.array_equal(frame, want) and
+                                                 np.array_equal(flat.reshape(L_, L_), want.astype(np.float64)))
+            if not row['bit_exact_vs_reference']:
+                raise RuntimeError("PSF drop-in differs from the reference kernel on the bench case")
+        out.append(row)
+    return out
+
+
 def run_native(args, wk):
     import torch
     import torch.distributed as dist
@@ -334,11 +552,14 @@ def run_native(args, wk):
     d0 = inp['depth0']
     mid0, half0 = 0.5 * (d0.max() + d0.min()), 0.5 * (d0.max() - d0.min())
     cheb_signal = ChebyshevSignal(np.c_[inp['lightcurve'] * mid0, inp['lightcurve'] * half0], (d0 - mid0) / half0)
+    # ... and as its two factors (bit-identical to the dense product)
+    from wayne_b200.lightcurve import SeparableSignal
+    sep_signal = SeparableSignal(inp['lightcurve'], inp['depth0'])
 
     def one(i, resident):
         eg = ExposureGenerator(*inp['eg_args'], filename='%04d_raw.fits' % (i + 1), rng='philox', device=local)
         kw = frame_kwargs(wk, rank * 100000 + i)
-        signal = depth_dev if resident is True else (cheb_signal if resident == 'driver' else depth_host)
+        signal = {True: depth_dev, 'driver': cheb_signal, 'separable': sep_signal}.get(resident, depth_host)
         resident = resident is True
         exp = eg.scanning_frame(kw.pop('x_ref'), kw.pop('y_ref'), kw.pop('x_jitter'), kw.pop('y_jitter'),
                                 wl_q, inp['flux'], signal,
@@ -476,6 +697,23 @@ def run_native(args, wk):
     ms_drv = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     gc.enable()
     h2d_drv = cheb_signal.coef.nbytes + cheb_signal.x.nbytes + inp['flux'].nbytes + inp['wl'].nbytes + 3 * 8 * N
+    # the planet signal as its two factors (lightcurve.SeparableSignal)
+    pipeline(0, max(12, args.warmup), 'separable')
+    barrier()
+    gc.collect()
+    gc.disable()
+    t0 = time.perf_counter()
+    s_issue, s_wait, _, _ = pipeline(n_warm, args.steps, 'separable')
+    ms_sep = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    gc.enable()
+    h2d_sep = 8 * (N + W) + inp['flux'].nbytes + inp['wl'].nbytes + 3 * 8 * N
+
+    # ---- BASELINE configs[4]: the multi-visit batch, exposure-wise over the ranks -------------
+    multi_visit = None
+    if not args.no_extras:
+        multi_visit = run_multi_visit(wk, inp, wl_q, local, rank, world, barrier, max_over_ranks,
+                                      n_visits=(8 if wk['photons'] >= 1e8 else 2),
+                                      n_exp=(128 if wk['photons'] >= 1e8 else 4))
     # per-kernel durations of the driver form (its k_counts evaluates the Chebyshev signal)
     eng.profile = True
     eng.stage_times()
@@ -557,29 +795,51 @@ def run_native(args, wk):
                                                         else 1965.0) * 1e6 / 4) / 1e9,
                   'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
     dominant = max(((k, v) for k, v in stages.items() if k.startswith('k_')), key=lambda kv: kv[1][0])[0]
+    ceiling = copy_ceiling_for(world)
+    e2e_val = world * 1e3 / ms_e2e
+
+    def frac_of(key, v):
+        c = (ceiling or {}).get('ceiling_exposures_per_s', {})
+        for k, cv in c.items():
+            if k.startswith(key) and cv:
+                return v / cv
+        return None
+
     line = {
         'metric': 'exposures_per_s', 'value': world * 1e3 / ms_value, 'unit': 'exposures/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_value,
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'warmup_performed': n_warm,
+        'ms_per_step': ms_value,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'photons_per_exposure': photons,
         'electron_bookkeeping': {'thrown': thrown, 'binned_in_frame': binned, 'dropped_off_frame': dropped,
                                  'check': 'binned + dropped == thrown over the timed exposures (asserted)'},
         'photons_per_s': world * photons * 1e3 / ms_value,
-        'config': {'workload': wk['desc'], 'n_subsamples': N, 'n_bins': W, 'rng': 'philox',
-                   'out_dtype': 'float64', 'window': [ww, wh], 'chunk_bins': chunk,
-                   'l2': 'no flush: per-exposure working set (planet signal 135 MB + interval planes 117 MB + dark 235 MB + reads 126 MB) exceeds the 126 MB L2'},
+        'config': bench_config(wk, N, W), 'rng': 'philox (native streams)', 'chunk_bins': chunk,
         'clocks': clocks,
-        'e2e': {'value': world * 1e3 / ms_e2e, 'unit': 'exposures/s', 'ms_per_step': ms_e2e,
+        'e2e': {'value': e2e_val, 'unit': 'exposures/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'form': 'planet signal = dense HOST array [n_samples][n_bins] (the reference\'s argument, '
+                        'uploaded every exposure); reads float64 to the host',
                 'host_issue_ms': [round(float(np.median(t_issue)), 3), round(float(np.max(t_issue)), 3)],
                 'host_wait_ms': [round(float(np.median(t_wait)), 3), round(float(np.max(t_wait)), 3)],
-                'host_step_ms': [round(a_ + b_, 2) for a_, b_ in zip(t_issue, t_wait)]},
-        'e2e_driver': {'value': world * 1e3 / ms_drv, 'unit': 'exposures/s', 'ms_per_step': ms_drv,
-                       'h2d_bytes_per_step': int(h2d_drv), 'd2h_bytes_per_step': int(d2h),
-                       'host_step_ms': [round(a_ + b_, 2) for a_, b_ in zip(d_issue, d_wait)],
-                       'host_issue_ms': [round(float(np.median(d_issue)), 3), round(float(np.max(d_issue)), 3)],
-                       'note': 'same exposure through Observation\'s form of the planet signal '
-                               '(lightcurve.ChebyshevSignal, evaluated inside k_counts): no 135 MB upload'},
+                'frac_of_copy_ceiling': frac_of('dense_host_signal', e2e_val),
+                'driver_form': {
+                    'value': world * 1e3 / ms_drv, 'unit': 'exposures/s', 'ms_per_step': ms_drv,
+                    'h2d_bytes_per_step': int(h2d_drv), 'd2h_bytes_per_step': int(d2h),
+                    'host_issue_ms': [round(float(np.median(d_issue)), 3), round(float(np.max(d_issue)), 3)],
+                    'frac_of_copy_ceiling': frac_of('factored_signal', world * 1e3 / ms_drv),
+                    'note': 'the same exposure with the planet signal in the visit driver\'s form '
+                            '(lightcurve.ChebyshevSignal, evaluated inside k_counts): what every exposure of '
+                            'Observation.run_observation does; no 135 MB upload'},
+                'separable_form': {
+                    'value': world * 1e3 / ms_sep, 'unit': 'exposures/s', 'ms_per_step': ms_sep,
+                    'h2d_bytes_per_step': int(h2d_sep), 'd2h_bytes_per_step': int(d2h),
+                    'host_issue_ms': [round(float(np.median(s_issue)), 3), round(float(np.max(s_issue)), 3)],
+                    'frac_of_copy_ceiling': frac_of('factored_signal', world * 1e3 / ms_sep),
+                    'note': 'planet signal handed over as its two factors (lightcurve.SeparableSignal: '
+                            'lightcurve[n_samples], depth[n_bins]); bit-identical frames to the dense array'},
+                'copy_ceiling': ceiling},
+        'multi_visit': multi_visit,
         'gpu_launches': int(launches), 'numa_bound': bool(numa_bound),
         'host_issue_ms': [round(float(np.median(v_issue)), 3), round(float(np.max(v_issue)), 3)],
         'stage_ms': {k: v[0] / args.steps for k, v in stages.items()},
@@ -591,14 +851,11 @@ def run_native(args, wk):
         'gather': ({'ms': t_gather, 'algorithmic_bytes': gather_bytes,
                     'achieved_gbs': gather_bytes / (t_gather * 1e-3) / 1e9} if t_gather else None),
     }
+    if world == 1 and not args.no_extras:
+        line['psf_dropin'] = run_psf_dropin(wk, inp)
     if world == 1 and not args.no_cpu:
         sec, info = cpu_reference_exposure(wk, inp, 48 * len(inp['read_index']))   # ~10-15 s of CPU work
-        line['cpu_baseline'] = {'value': 1.0 / sec, 'unit': 'exposures/s', 'cores': info['cores'],
-                                'kind': info['kind'], 'sample': info['sample'],
-                                'photons_per_s': info['photons_per_exposure'] / sec,
-                                'native_kernel_alone': info['psf_alone'],
-                                'note': 'lower bound on the reference time: numpy restatement without astropy '
-                                        'unit algebra, calibration FITS read once instead of per read'}
+        line['cpu_baseline'] = cpu_baseline_object(1.0 / sec, info)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -612,12 +869,12 @@ def main():
     ap.add_argument('--impl', default='native', choices=('native', 'reference'))
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extras', action='store_true', help='skip the multi-visit and PSF drop-in legs')
+    ap.add_argument('--no-full', action='store_true',
+                    help='reference arm: bounded samples only (no full un-sampled exposure as step 1)')
     args = ap.parse_args()
     wk = WORKLOADS[args.workload]
     if args.impl == 'reference':
-        if args.steps > 3:
-            args.steps = 3          # bounded: each step is ~10-20 s of CPU work
-        args.warmup = min(args.warmup, 1)
         run_reference(args, wk)
     else:
         if args.warmup < 3:

@@ -34,7 +34,8 @@
 namespace wb {
 int launch_reads(const wb200_reads_args *a, cudaStream_t st);   // wayne_b200.cu
 int launch_counts(const wb200_counts_args *a, cudaStream_t st); // wayne_b200.cu
-int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct);
+int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct,
+                  int n_split);
 
 // electrons thrown / binned / dropped of one exposure, for the caller's bookkeeping
 __global__ void __launch_bounds__(256)
@@ -621,7 +622,7 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
         ga.d_flat[i] = (const double *)c->planes[WB200_PLANE_FLAT0 + i].d;
     ga.d_acc = (double *)c->acc.d;
     mark_begin(c, 3, st);
-    CTX_STAGE(c, throw_photons(&pa, 0, st, &ga));
+    CTX_STAGE(c, throw_photons(&pa, 0, st, &ga, 1));
     mark_end(c, st);
 
     // ---- the per-pixel ramp pass ---------------------------------------------------------------

@@ -97,6 +97,7 @@ __device__ inline void randr_normals(long long e, long long ssum, int T, int tes
 struct PhotonParams {
     wb200_photon_args a;
     int sample0; // global index of the launch's first sub-sample (Philox counters)
+    int n_split; // generic kernel: CTAs sharing one chunk's electrons (grid.z)
 };
 
 template <int TW, int TH>
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
             const float fx = (float)(bx - (double)T.x0);
             const float fy = (float)(by - (double)T.y0);
             const float fsl = (float)bsl * WB_SQRT_2LN2, fsh = (float)bsh * WB_SQRT_2LN2;
-            for (int base = 0; base < total; base += 32) {
+            for (int base = 32 * (int)blockIdx.z; base < total; base += 32 * (int)gridDim.z) {
                 const int q = base + lane;
                 int b = 0;
 #pragma unroll
@@ -471,7 +472,9 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
             if (MODE == WB200_RNG_HOST)
                 An = a.d_normals + a.d_normals_base[s_local];
             const int test = (MODE == WB200_RNG_RANDR) ? a.d_seeds[s_local] : 0;
-            for (int base = 0; base < total; base += 32) {
+            // (gridDim.z CTAs share a chunk's electron stream in rows of 32: few bins and many
+            // electrons -- one PSF() call -- still fill the machine; integer adds commute)
+            for (int base = 32 * (int)blockIdx.z; base < total; base += 32 * (int)gridDim.z) {
                 const int q = base + lane;
                 int b = 0;
 #pragma unroll

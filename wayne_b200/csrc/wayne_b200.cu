@@ -55,14 +55,15 @@ static int launch_throw(const PhotonParams &p, cudaStream_t st)
 {
     const wb200_photon_args &a = p.a;
     const int chunks = (a.n_bins + a.chunk_bins - 1) / a.chunk_bins;
-    dim3 grid(chunks, a.n_samples);
+    dim3 grid(chunks, a.n_samples, p.n_split > 1 ? p.n_split : 1);
     const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int);
     k_throw<MODE, TILE_W, TILE_H><<<grid, 256, smem, st>>>(p);
     WB_LAUNCHED("k_throw");
     return WB200_OK;
 }
 
-int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct)
+int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct,
+                  int n_split = 1)
 {
     WB_REQUIRE(a != nullptr, "null args");
     WB_REQUIRE(a->n_samples >= 0 && a->n_bins > 0, "bad sizes");
@@ -77,6 +78,7 @@ int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, cons
     PhotonParams p;
     p.a = *a;
     p.sample0 = sample0;
+    p.n_split = n_split;
     WB_REQUIRE(!direct || a->rng_mode == WB200_RNG_PHILOX, "direct accumulation is a native-mode path");
     switch (a->rng_mode) {
     case WB200_RNG_PHILOX: {
@@ -209,19 +211,6 @@ int launch_reads(const wb200_reads_args *a, cudaStream_t st)
 
 using namespace wb;
 
-namespace {
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf()
-    {
-        if (p)
-            cudaFree(p);
-    }
-    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
-    template <typename T>
-    T *as() { return (T *)p; }
-};
-} // namespace
 
 extern "C" {
 
@@ -404,6 +393,47 @@ int wb200_reads(const wb200_reads_args *args, void *stream) { return launch_read
 // PSF drop-in (wayne/pyparallel_menu.c:10-113): host buffers in, host frame out.
 // ---------------------------------------------------------------------------
 
+namespace {
+// Per-thread scratch of the PSF() drop-in: device buffers, pinned staging and a stream that
+// live as long as the calling thread, so a call costs one host->device copy, the kernels and
+// one device->host copy -- not seven cudaMalloc / cudaFree pairs and eight pageable copies.
+struct PsfScratch {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    char *h_in = nullptr, *d_in = nullptr;
+    size_t in_cap = 0;
+    int *h_out = nullptr, *d_win = nullptr;
+    size_t out_cap = 0;
+    int32_t *d_off = nullptr;
+    size_t off_cap = 0;
+    double *d_norm = nullptr;
+    size_t norm_cap = 0;
+    void release()
+    {
+        if (device < 0)
+            return;
+        if (h_in)
+            cudaFreeHost(h_in);
+        if (h_out)
+            cudaFreeHost(h_out);
+        for (void *p : {(void *)d_in, (void *)d_win, (void *)d_off, (void *)d_norm})
+            if (p)
+                cudaFree(p);
+        if (st)
+            cudaStreamDestroy(st);
+        *this = PsfScratch();
+    }
+    ~PsfScratch() { release(); }
+};
+thread_local PsfScratch g_psf;
+
+struct PsfHeader { // travels in front of the packed inputs
+    uint64_t lost, total;
+    int32_t ox, oy, seed, pad;
+    int64_t nbase;
+};
+} // namespace
+
 int wb200_psf_host(const int *counts, int size, const double *x_pos, const double *y_pos,
                    const double *psf_ratio, const double *psf_sigmal, const double *psf_sigmah,
                    int nr, int nc, int test, int threads, int rng_mode, const double *normals,
@@ -424,38 +454,74 @@ int wb200_psf_host(const int *counts, int size, const double *x_pos, const doubl
         ssum += counts[i] > 0 ? counts[i] : 0;
     WB_REQUIRE(ssum < 2147483647LL, "more than 2^31-1 electrons (the reference's int overflows too)");
 
+    PsfScratch &S = g_psf;
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (S.device != dev) {
+        S.release();
+        WB_CUDA(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+        S.device = dev;
+    }
     const size_t nb = (size_t)size;
-    DevBuf d_counts, d_off, d_tot, d_dbl, d_win, d_misc, d_norm;
-    if (d_counts.alloc(nb * 4) || d_off.alloc(nb * 4) || d_tot.alloc(8) || d_dbl.alloc(nb * 8 * 5) ||
-        d_win.alloc(npix * 4) || d_misc.alloc(64))
-        return fail(WB200_ERR_NOMEM, "cudaMalloc failed%s%s");
-    cudaStream_t st = 0;
-    // negative counts never throw (the reference's loops simply do not run)
-    std::vector<int> cpos(counts, counts + size);
-    for (auto &c : cpos)
-        if (c < 0)
-            c = 0;
-    WB_CUDA(cudaMemcpyAsync(d_counts.p, cpos.data(), nb * 4, cudaMemcpyHostToDevice, st));
-    double *dd = d_dbl.as<double>();
+    // packed inputs: header | counts int32 [nb] (padded to 8) | x, y, ratio, sigl, sigh double [nb] each
+    const size_t off_counts = sizeof(PsfHeader);
+    const size_t off_dbl = off_counts + (nb * 4 + 7) / 8 * 8;
+    const size_t in_bytes = off_dbl + nb * 8 * 5;
+    if (S.in_cap < in_bytes) {
+        if (S.h_in)
+            cudaFreeHost(S.h_in);
+        if (S.d_in)
+            cudaFree(S.d_in);
+        S.h_in = S.d_in = nullptr;
+        S.in_cap = 0;
+        const size_t cap = in_bytes + in_bytes / 2 + 4096;
+        WB_CUDA(cudaHostAlloc((void **)&S.h_in, cap, cudaHostAllocDefault));
+        WB_CUDA(cudaMalloc((void **)&S.d_in, cap));
+        S.in_cap = cap;
+    }
+    if (S.out_cap < npix) {
+        if (S.h_out)
+            cudaFreeHost(S.h_out);
+        if (S.d_win)
+            cudaFree(S.d_win);
+        S.h_out = S.d_win = nullptr;
+        S.out_cap = 0;
+        WB_CUDA(cudaHostAlloc((void **)&S.h_out, npix * sizeof(int), cudaHostAllocDefault));
+        WB_CUDA(cudaMalloc((void **)&S.d_win, npix * sizeof(int)));
+        S.out_cap = npix;
+    }
+    if (S.off_cap < nb) {
+        if (S.d_off)
+            cudaFree(S.d_off);
+        S.d_off = nullptr;
+        S.off_cap = 0;
+        WB_CUDA(cudaMalloc((void **)&S.d_off, (nb + nb / 2 + 256) * 4));
+        S.off_cap = nb + nb / 2 + 256;
+    }
+    PsfHeader hd = {0, (uint64_t)ssum, 0, 0, test, 0, 0};
+    memcpy(S.h_in, &hd, sizeof(hd));
+    int32_t *hc = (int32_t *)(S.h_in + off_counts);
+    for (size_t i = 0; i < nb; ++i) // negative counts never throw (the reference's loops simply do not run)
+        hc[i] = counts[i] > 0 ? counts[i] : 0;
     const double *src[5] = {x_pos, y_pos, psf_ratio, psf_sigmal, psf_sigmah};
     for (int i = 0; i < 5; ++i)
-        WB_CUDA(cudaMemcpyAsync(dd + i * nb, src[i], nb * 8, cudaMemcpyHostToDevice, st));
-    const uint64_t tot = (uint64_t)ssum;
-    WB_CUDA(cudaMemcpyAsync(d_tot.p, &tot, 8, cudaMemcpyHostToDevice, st));
-    // misc: [0] lost (u64) [8] ox [12] oy [16] seed [24] normals_base (i64)
-    struct {
-        uint64_t lost;
-        int32_t ox, oy, seed, pad;
-        int64_t nbase;
-    } misc = {0, 0, 0, test, 0, 0};
-    WB_CUDA(cudaMemcpyAsync(d_misc.p, &misc, sizeof(misc), cudaMemcpyHostToDevice, st));
-    WB_CUDA(cudaMemsetAsync(d_win.p, 0, npix * 4, st));
+        memcpy(S.h_in + off_dbl + (size_t)i * nb * 8, src[i], nb * 8);
+    cudaStream_t st = S.st;
+    WB_CUDA(cudaMemcpyAsync(S.d_in, S.h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemsetAsync(S.d_win, 0, npix * 4, st));
     if (rng_mode == WB200_RNG_HOST) {
-        if (d_norm.alloc((size_t)ssum * 2 * 8))
-            return fail(WB200_ERR_NOMEM, "cudaMalloc failed%s%s");
-        WB_CUDA(cudaMemcpyAsync(d_norm.p, normals, (size_t)ssum * 2 * 8, cudaMemcpyHostToDevice, st));
+        const size_t n = (size_t)ssum * 2;
+        if (S.norm_cap < n) {
+            if (S.d_norm)
+                cudaFree(S.d_norm);
+            S.d_norm = nullptr;
+            S.norm_cap = 0;
+            WB_CUDA(cudaMalloc((void **)&S.d_norm, (n ? n : 1) * 8));
+            S.norm_cap = n ? n : 1;
+        }
+        WB_CUDA(cudaMemcpyAsync(S.d_norm, normals, n * 8, cudaMemcpyHostToDevice, st));
     }
-    int rc = wb200_count_offsets(1, size, d_counts.as<int32_t>(), d_off.as<int32_t>(), st);
+    int rc = wb200_count_offsets(1, size, (const int32_t *)(S.d_in + off_counts), S.d_off, st);
     if (rc)
         return rc;
 
@@ -463,9 +529,24 @@ int wb200_psf_host(const int *counts, int size, const double *x_pos, const doubl
     memset(&a, 0, sizeof(a));
     a.n_samples = 1;
     a.n_bins = size;
-    // enough CTAs to fill the machine, chunks a multiple of 32 bins
-    int chunk = ((size + 591) / 592 + 31) / 32 * 32;
+    // One sub-sample must still fill 148 SMs: chunks of at most 256 bins (a CTA's eight warps
+    // take a 32-bin group each), and the electron stream of a chunk shared by n_split CTAs so
+    // that ~4 warps per scheduler are busy whatever the number of bins.
+    int chunk = ((size + 147) / 148 + 31) / 32 * 32;
+    if (chunk > 256)
+        chunk = 256;
     a.chunk_bins = chunk < 32 ? 32 : chunk;
+    const int chunks = (size + a.chunk_bins - 1) / a.chunk_bins;
+    const long long groups = (size + 31) / 32;
+    long long n_split = (148LL * 16 + groups - 1) / groups;                       // target ~2400 busy warps
+    const long long by_work = (ssum / 32 + groups * 8 - 1) / (groups * 8 > 0 ? groups * 8 : 1); // >= 8 rows of 32 electrons per warp
+    if (n_split > by_work)
+        n_split = by_work;
+    if (n_split < 1)
+        n_split = 1;
+    if (n_split > 64)
+        n_split = 64;
+    (void)chunks;
     a.nr = nr;
     a.nc = nc;
     a.rng_mode = rng_mode;
@@ -475,31 +556,32 @@ int wb200_psf_host(const int *counts, int size, const double *x_pos, const doubl
     a.sub_scale = 0.0;
     a.key0 = (uint32_t)test;
     a.key1 = 0x57415945u; // "WAYE"
-    a.d_counts = d_counts.as<int32_t>();
-    a.d_offsets = d_off.as<int32_t>();
-    a.d_totals = d_tot.as<uint64_t>();
+    a.d_counts = (const int32_t *)(S.d_in + off_counts);
+    a.d_offsets = S.d_off;
+    PsfHeader *dh = (PsfHeader *)S.d_in;
+    a.d_totals = &dh->total;
+    const double *dd = (const double *)(S.d_in + off_dbl);
     a.d_xpos = dd;
     a.d_ypos = dd + nb;
     a.d_ratio = dd + 2 * nb;
     a.d_sigl = dd + 3 * nb;
     a.d_sigh = dd + 4 * nb;
-    char *m = d_misc.as<char>();
-    a.d_lost = (uint64_t *)m;
-    a.d_win_ox = (int32_t *)(m + 8);
-    a.d_win_oy = (int32_t *)(m + 12);
-    a.d_seeds = (int32_t *)(m + 16);
-    a.d_normals_base = (int64_t *)(m + 24);
-    a.d_normals = d_norm.as<double>();
-    a.d_win = d_win.as<int32_t>();
-    rc = throw_photons(&a, 0, st, nullptr);
+    a.d_lost = &dh->lost;
+    a.d_win_ox = &dh->ox;
+    a.d_win_oy = &dh->oy;
+    a.d_seeds = &dh->seed;
+    a.d_normals_base = &dh->nbase;
+    a.d_normals = S.d_norm;
+    a.d_win = S.d_win;
+    rc = throw_photons(&a, 0, st, nullptr, rng_mode == WB200_RNG_PHILOX ? 1 : (int)n_split);
     if (rc)
         return rc;
-    WB_CUDA(cudaMemcpyAsync(frame_out, d_win.p, npix * 4, cudaMemcpyDeviceToHost, st));
-    uint64_t lost = 0;
-    WB_CUDA(cudaMemcpyAsync(&lost, d_misc.p, 8, cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaMemcpyAsync(S.h_out, S.d_win, npix * 4, cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaMemcpyAsync(S.h_in, S.d_in, sizeof(PsfHeader), cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaStreamSynchronize(st));
-    if (lost)
+    if (((PsfHeader *)S.h_in)->lost)
         return fail(WB200_ERR_LOST, "electrons fell outside the frame window%s%s");
+    memcpy(frame_out, S.h_out, npix * sizeof(int));
     return WB200_OK;
 }
 
