@@ -578,6 +578,11 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     if (c->chunk_bins == 0 || c->chunk_W != W || c->chunk_N != N || c->chunk_wl0 != a->wl[0] ||
         c->chunk_wl1 != a->wl[W - 1]) {
         c->chunk_bins = choose_chunk_bins(I, *a);
+        if (const char *env = getenv("WB200_CHUNK_BINS")) { // A/B switch (a multiple of 32)
+            const int v = atoi(env) / 32 * 32;
+            if (v >= 32)
+                c->chunk_bins = v;
+        }
         c->chunk_W = W;
         c->chunk_N = N;
         c->chunk_wl0 = a->wl[0];

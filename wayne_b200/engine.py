@@ -914,6 +914,12 @@ class ContextRun(object):
         return self.stats[0]
 
     def photons(self):
+        """Electrons thrown (incl. those landing off-frame).  When the exposure's reads were
+        fetched to the host the statistics travelled with them: no device synchronisation."""
+        host = getattr(self, 'stats_host', None)
+        if host is not None:
+            self.stats_done.synchronize()
+            return int(host[0])
         return int(self.stats[0].item())
 
     def counts_host(self):
@@ -982,10 +988,33 @@ class ExposureContext(object):
         self._upload(_lib.PLANE_SENS_WL, np.ascontiguousarray(sens_wl, dtype=np.float64), _lib.F64)
         self._upload(_lib.PLANE_SENS_VAL, np.ascontiguousarray(sens_val, dtype=np.float64), _lib.F64)
 
+    keep_host_copies = False     # tests: remember what was uploaded / passed (write_bundle)
+
     def _upload(self, which, arr, dtype):
         self._check(lib.wb200_ctx_upload_plane(self._h, which, C.c_void_p(arr.ctypes.data), dtype, arr.size),
                     "wb200_ctx_upload_plane")
         self._have.add(which)
+        if self.keep_host_copies:
+            self.__dict__.setdefault('_uploaded', {})[which] = (arr, dtype)
+
+    def write_bundle(self, path):
+        """Everything a C host needs to repeat the LAST exposure of this context, as the flat record
+        file examples/c_host/exposure_host.c reads (needs keep_host_copies = True beforehand)."""
+        import struct
+        a, host = self._last_args
+        tags = dict(wl=110, flux=111, xref=112, yref=113, dur_ms=114, dt_s=115, read_end=116, sep_row=117,
+                    sep_col=118, cos_pixel=119, cos_read=120, cos_energy=121)
+        with open(path, 'wb') as f:
+            def rec(tag, dtype, arr):
+                arr = np.ascontiguousarray(arr)
+                f.write(struct.pack('<iiq', tag, dtype, arr.size))
+                f.write(arr.tobytes())
+            for which, (arr, dtype) in sorted(self._uploaded.items()):
+                rec(which, 1 if dtype == _lib.F64 else 0, arr)
+            rec(100, 3, np.frombuffer(bytes(self._inst), dtype=np.uint8))
+            rec(101, 3, np.frombuffer(bytes(a), dtype=np.uint8))
+            for name, arr in host.items():
+                rec(tags[name], {np.dtype(np.float64): 1, np.dtype(np.int32): 2}[arr.dtype], arr)
 
     def ensure_planes(self, add_flat, sky, gain, nonlinear, dark_reads, zero_read):
         """Upload (once) the planes the requested terms read.  dark_reads = number of reads
@@ -1056,23 +1085,28 @@ class ExposureContext(object):
         a.noise_mean, a.noise_std = float(noise[0] or 0.0), float(noise[1] or 0.0)
         keep = []          # host arrays must stay alive until the call has copied them (it does before returning)
 
-        def host(arr, dtype=np.float64):
+        named = {}
+
+        def host(arr, dtype=np.float64, name=None):
             arr = np.ascontiguousarray(arr, dtype=dtype)
             keep.append(arr)
+            if name:
+                named[name] = arr
             return C.c_void_p(arr.ctypes.data)
 
-        a.wl, a.xref, a.yref, a.dur_ms = host(wl_um), host(xr), host(yr), host(dur_ms)
-        a.dt_s, a.read_end = host(dt_s), host(read_end, np.int32)
+        a.wl, a.xref, a.yref = host(wl_um, name='wl'), host(xr, name='xref'), host(yr, name='yref')
+        a.dur_ms, a.dt_s = host(dur_ms, name='dur_ms'), host(dt_s, name='dt_s')
+        a.read_end = host(read_end, np.int32, name='read_end')
         if isinstance(flux, torch.Tensor):
             keep.append(flux)
             a.d_flux = flux.data_ptr()
         else:
-            a.flux = host(flux)
+            a.flux = host(flux, name='flux')
         slot = None
         if depth is not None:
             if hasattr(depth, 'row') and hasattr(depth, 'col'):          # lightcurve.SeparableSignal
-                a.sep_row = host(depth.row[:N])
-                a.sep_col = host(depth.col[depth_col0:depth_col0 + W])
+                a.sep_row = host(depth.row[:N], name='sep_row')
+                a.sep_col = host(depth.col[depth_col0:depth_col0 + W], name='sep_col')
             elif hasattr(depth, 'coef') and hasattr(depth, 'x'):          # lightcurve.ChebyshevSignal
                 a.cheb_order = int(depth.coef.shape[1])
                 a.cheb_x = host(depth.x[depth_col0:depth_col0 + W])
@@ -1104,8 +1138,9 @@ class ExposureContext(object):
                     a.d_depth = d_depth.data_ptr() + 8 * int(depth_col0)
         if cosmics is not None and len(cosmics[0]):
             a.n_cosmics = len(cosmics[0])
-            a.cos_pixel, a.cos_read = host(cosmics[0], np.int32), host(cosmics[1], np.int32)
-            a.cos_energy = host(cosmics[2])
+            a.cos_pixel = host(cosmics[0], np.int32, name='cos_pixel')
+            a.cos_read = host(cosmics[1], np.int32, name='cos_read')
+            a.cos_energy = host(cosmics[2], name='cos_energy')
         stats = e.empty((4,), torch.int64)
         a.d_stats = stats.data_ptr()
         out = e.empty((R + 1, self.F, self.F), torch.float32 if out_f32 else torch.float64)
@@ -1116,4 +1151,6 @@ class ExposureContext(object):
         e.mark('exposure', False)
         if slot is not None:
             e.release_upload(slot)
+        if self.keep_host_copies:
+            self._last_args = (a, named)
         return out, ContextRun(self, N, W, R, stats)

@@ -490,11 +490,11 @@ class ExposureGenerator(object):
                            add_read_noise, zero_read is not None, noise, cosmics,
                            np.dtype(out_dtype) == np.float32)
         self._run = run
-        return self._hand_over(eng, out, None, device_result, start_time, read_times_s, zero_read_info,
-                               len(xr), progress_bar)
+        return self._hand_over(eng, out, run.stats, device_result, start_time, read_times_s, zero_read_info,
+                               len(xr), progress_bar, stats_of=run)
 
     def _hand_over(self, eng, out, lost, device_result, start_time, read_times_s, zero_read_info,
-                   num_samples, progress_bar):
+                   num_samples, progress_bar, stats_of=None):
         """Leave the reads in HBM (device_result) or queue the single device->host copy into
         pooled pinned memory; exposure.reads waits for it on first access."""
         from . import _lib
@@ -506,6 +506,11 @@ class ExposureGenerator(object):
             return self.exposure
         done, reads_host, lost = eng.fetch_async(out, small=lost)
         nsamp = self.NSAMP
+        if stats_of is not None:
+            # the context path's small tensor is the exposure's statistics (thrown / binned /
+            # dropped electrons), not a lost-electron counter: it rides the same download
+            stats_of.stats_host, stats_of.stats_done = lost, done
+            lost = None
 
         def materialize(exp):
             done.synchronize()
