@@ -2,7 +2,7 @@
 default workload `c4`): G141 spatial scan, SUBARRAY 1024 (F = 1024, L = 1014, the
 -5 flat / sub-array offset), NSAMP 15 RAPID (R = 14 read intervals), 10 ms
 sub-samples (N = 4116), W = 4096 bins -- the geometry of wayne/exposure_generator.py:
-336-394 that smaller cases do not reach: bin chunking at 1376 bins per CTA, the
+336-394 that smaller cases do not reach: bin chunking at 1376 / 2048 bins per CTA, the
 read-interval assignment over 14 planes, the int64 fixed-point planes near 1e9
 electrons.
 
@@ -93,7 +93,7 @@ def test_c4_native_conserves_every_electron(calb_dir):
     run = eg._run
     counts = run.counts_host().astype(np.int64)
     assert counts.shape == (4116, 4096) and 9.7e8 < counts.sum() < 1.03e9
-    assert run.win_geometry[2] == 1376
+    assert run.win_geometry[2] == 2048
     ints = np.rint(planes)
     assert np.max(np.abs(planes - ints)) < 1e-6         # whole electrons in every pixel
     first = 0

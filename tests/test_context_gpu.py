@@ -143,3 +143,30 @@ def test_context_refuses_bad_input(calb_dir):
     bad = np.array([0.1 + 1e-12], dtype=np.float64)                 # not float32-representable
     rc = _lib.lib.wb200_ctx_upload_plane(ctx._h, _lib.PLANE_SKY, C.c_void_p(bad.ctypes.data), _lib.F64, 1)
     assert rc == -1 and b"float32" in _lib.lib.wb200_ctx_last_error(ctx._h)
+
+
+def test_stated_limits_are_enforced_and_accounted_for(calb_dir):
+    """(1) more than 65535 sub-samples per exposure (grid.y of the kernels) is refused with a
+    message, not truncated; (2) bins whose position is beyond the +-2^22 px range of the
+    thrower's magic-add floor (or NaN) throw nothing and every one of their electrons is
+    accounted as dropped: binned + dropped == thrown still holds exactly."""
+    from wayne import detector, grism
+    from wayne import units as u
+    from wayne.exposure_generator import ExposureGenerator
+    from wayne_b200 import _lib
+    wl, flux, planet = harness.spectrum(level=2.0e-14)
+    eg = ExposureGenerator(detector.WFC3_IR(), grism.G141(), 5, 'SPARS10', 256, None, rng='philox')
+    with pytest.raises(_lib.WayneB200Error, match="65535"):
+        eg.scanning_frame(404.5, 457.4, 0.02, 0.02, wl * u.micron, flux, None, 7.4325 * u.pixel / u.s,
+                          0.3 * u.ms, cosmic_rate=None)                      # 74 000 sub-samples
+    for x_ref in (2.0e7, -9.0e6, float('nan')):
+        eg = ExposureGenerator(detector.WFC3_IR(), grism.G141(), 5, 'SPARS10', 256, None, rng='philox')
+        exp = eg.scanning_frame(x_ref, 457.4, 0.0, 0.0, wl * u.micron, flux, None, 7.4325 * u.pixel / u.s,
+                                400 * u.ms, cosmic_rate=None, sky_background=0 * u.count / u.s, add_dark=False,
+                                add_non_linear=False, add_read_noise=False, add_initial_bias=False, rng_key=(3, 3))
+        stats = eg._run.stats.cpu().numpy()
+        if np.isnan(x_ref):
+            assert stats[1] == 0 and stats[1] + stats[2] == stats[0]         # NaN positions: nothing binned
+        else:
+            assert stats[0] > 1e6 and stats[1] == 0 and stats[2] == stats[0]
+        assert np.all(np.array([r[0] for r in exp.reads]) == 0)

@@ -183,8 +183,11 @@ inline int ctx_reserve(wb200_ctx *c, wb200_ctx::Buf &b, size_t bytes, bool zero 
     return WB200_OK;
 }
 
-// Bins per CTA of the thrower: the chunk's trace segment plus 4 sigma of the wide Gaussian must
-// fit the 128-pixel shared tile; equal chunks; at least ~16 CTAs per SM in the grid.  The trace
+// Bins per CTA of the thrower: the chunk's trace segment plus 3 sigma of the wide Gaussian either
+// side must fit the 128-pixel shared tile (the few electrons of the end bins that leave it are
+// replayed; fewer, longer CTAs pay the tile zeroing / placement / flush less often: 2048 bins per
+// CTA measured 1.91 ms, 1376 1.97, 1024 2.01, 512 2.24 on the configs[3] shape); equal chunks; at
+// least ~16 CTAs per SM in the grid.  The trace
 // length depends on the grism and the wavelength grid, hardly on the pointing: evaluated on every
 // (N/32)-th sub-sample and cached per (W, N, wavelength range).
 inline int choose_chunk_bins(const wb200_instrument &I, const wb200_exposure_args &a)
@@ -221,7 +224,7 @@ inline int choose_chunk_bins(const wb200_instrument &I, const wb200_exposure_arg
             extent = fmax(extent, fabs(xb - xa));
     }
     extent += 1.0;
-    const double core = fmax(8.0, 128.0 - 2.0 * 4.0 * sig);
+    const double core = fmax(8.0, 128.0 - 2.0 * 3.0 * sig);
     long long chunk = extent > core ? (long long)(W * core / extent) : W;
     chunk = chunk / 32 * 32;
     if (chunk < 32)
