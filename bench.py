@@ -773,7 +773,7 @@ def run_native(args, wk):
         rng_peak = atom_psf = atom_free = philox_calls = imad_wide = None
     traffic = {}
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
             traffic = json.load(f)
     except Exception:      # noqa: BLE001
         pass
