@@ -125,7 +125,7 @@ def frame_kwargs(wk, i):
     return dict(x_ref=wk['x_ref'] + 0.02 * rw.standard_normal(), y_ref=wk['y_ref'] + 0.02 * rw.standard_normal(),
                 x_jitter=0.025, y_jitter=0.025, scan_speed=wk['scan'] * u.pixel / u.s,
                 sample_rate=wk['rate'] * u.ms, ssv_generator=SSVSine(1.5, 1.1, 0), cosmic_rate=11.,
-                sky_background=5.5 * u.count / u.s, scale_factor=1.0 - 1e-4 * i)
+                sky_background=5.5 * u.count / u.s, scale_factor=1.0 - 1e-4 * (i % 100))   # (i carries rank * 100000)
 
 
 class ClockSampler(object):
@@ -585,7 +585,7 @@ def run_native(args, wk):
     # (the NVML sampler thread is started before the warm-up so its start-up cost
     # is outside the timed region; its samples are reset when the clock starts)
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('WB200_NO_CLOCKS')) else None
-    eng.profile = True               # stage events on in the warm-up too (first-use costs)
+    eng.profile = False              # the warm-up runs like the timed region (see below)
     phot_acc = torch.zeros((), dtype=torch.int64, device=dev)
     lost_acc = torch.zeros((1,), dtype=torch.int64, device=dev)
     tally_acc = torch.zeros((2,), dtype=torch.int64, device=dev)
@@ -603,7 +603,11 @@ def run_native(args, wk):
     tune_host()                      # gc.freeze(): no 40 ms full-GC pauses inside the timed regions
     if sampler:
         sampler.reset()
-    eng.profile = True
+    # per-stage CUDA events are OFF inside the timed region: with them on the library keeps every
+    # kernel of an exposure on one stream (wb200_exposure_run), without them consecutive exposures
+    # overlap (the next exposure's tables and counts run beside this one's electron throw).  The
+    # per-kernel durations are measured right after it, on the same inputs, one kernel at a time.
+    eng.profile = False
     eng.stage_times()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -637,6 +641,12 @@ def run_native(args, wk):
     if os.environ.get('WB200_HOSTTRACE'):
         sys.stderr.write('[hosttrace] t=%.1f VALUE REGION END\n' % (time.perf_counter() * 1e3 % 1e6))
     ms_value = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    eng.profile = True
+    eng.stage_times()
+    n_prof = max(4, min(args.steps, 12))
+    for i in range(n_prof):
+        eg, _ = one(n_warm + args.steps + i, True)
+        del eg
     stages = eng.stage_times()
     eng.profile = False
     clocks = sampler.stop() if sampler else None
@@ -733,7 +743,7 @@ def run_native(args, wk):
     S = wk['sub']
     F = min(S + 10, 1024)
     R = wk['nsamp'] - 1
-    per = lambda name: (stages[name][0] / args.steps) if name in stages else None   # noqa: E731
+    per = lambda name: (stages[name][0] / max(1, stages[name][1])) if name in stages else None   # noqa: E731
     hbm_peak, peak_src = measured_peaks()
     from wayne_b200 import params as _p
     pb = 4 if (_p.use_context and _p.direct_accumulation) else 8    # resident planes: float32 through the context
@@ -842,7 +852,9 @@ def run_native(args, wk):
         'multi_visit': multi_visit,
         'gpu_launches': int(launches), 'numa_bound': bool(numa_bound),
         'host_issue_ms': [round(float(np.median(v_issue)), 3), round(float(np.max(v_issue)), 3)],
-        'stage_ms': {k: v[0] / args.steps for k, v in stages.items()},
+        'stage_ms': {k: v[0] / max(1, v[1]) for k, v in stages.items()},
+        'stage_ms_note': 'one kernel at a time (per-stage events keep an exposure on one stream), %d exposures '
+                         'right after the timed region; inside it consecutive exposures overlap' % n_prof,
         'stage_ms_driver': {k: v[0] / max(1, v[1]) for k, v in stages_drv.items()},
         'dominant_kernel': dominant,
         'roofline': roof_throw if dominant == 'k_throw' else roof_hbm,

@@ -361,7 +361,14 @@ int wb200_cosmic_chains(int n_hits, const int32_t *d_pixel, int32_t n_pixels,
  * thread) has the message.  Nothing throws across the boundary.
  * wb200_exposure_run is asynchronous on `stream`: it returns when the work is
  * queued.  Host arrays passed to it are copied before it returns and may be
- * reused immediately.
+ * reused immediately.  The output (and d_stats) is complete in `stream` order.
+ * Consecutive exposures overlap on the device: the tables, traces and counts of
+ * an exposure (stage 1) are made on a stream of the context's own, into the
+ * other of two scratch lanes, while the previous exposure's electrons are still
+ * being thrown on `stream` -- its electron throw and ramp pass then follow on
+ * `stream` as before.  Results do not depend on it (same counters, same
+ * kernels); WB200_CTX_SERIAL=1 in the environment at context creation, or
+ * per-stage timing (wb200_ctx_profile), keeps everything on `stream`.
  * -------------------------------------------------------------------------- */
 typedef struct wb200_ctx wb200_ctx;
 
@@ -423,7 +430,10 @@ typedef struct wb200_exposure_args {
         add_zero, add_noise;    /* the switches of scanning_frame (exposure_generator.py:178-192) */
     int32_t out_f32;            /* 0: float64 reads like the reference, 1: float32   */
     uint32_t key0, key1;        /* Philox key of the exposure                        */
-    int32_t pad0;
+    int32_t device_inputs_ready; /* 1: d_flux / d_depth / d_cheb_coef (if any) are complete already --   */
+                                /* nothing queued on `stream` produces them -- so the library may     */
+                                /* start this exposure's tables and counts on its own stream while the */
+                                /* previous exposure is still running; 0: ordered after `stream`       */
     double scale;               /* visit-trend scale factor (:620-621)               */
     double sky_rate;            /* counts/s                                          */
     double noise_mean, noise_std;
@@ -490,9 +500,10 @@ int wb200_microbench(int which, int iters, double *ms_out, double *ops_out);
  *   which = 0: Philox4x32-10 (Salmon et al., SC'11) of counter c[4] under key k[2], the
  *              function behind the count / per-pixel samplers: the Random123 known-answer
  *              vectors apply (tests/test_rng_gpu.py);
- *   which = 1: the native thrower's call for unit c[0] of bin c[2] in sub-sample c[1] of the
- *              exposure keyed k[2], stream id c[3] (2 electrons, 7 their tail refinement):
- *              fixed-key Philox4x32-10 over (unit, hy + sub-sample, bin, hw ^ stream) with
+ *   which = 1: the native thrower's call with first counter word c[0] (the thrower passes 4 x the
+ *              unit index = the index of the unit's first electron) for bin c[2] in sub-sample c[1]
+ *              of the exposure keyed k[2], stream id c[3] (2 electrons, 7 their tail refinement):
+ *              fixed-key Philox4x32-10 over (c[0], hy + sub-sample, bin, hw ^ stream) with
  *              (hy, hw) = splitmix64 of the key; out[4], out[5] return hy, hw. */
 int wb200_philox_words(int which, const uint32_t *c, const uint32_t *k, uint32_t *out);
 

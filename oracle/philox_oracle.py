@@ -10,7 +10,8 @@ INFRASTRUCTURE ONLY (see oracle/__init__.py): the product never imports this.
   and this oracle pins the generator underneath it.)
 * ``throw_keys`` / ``thrower_words`` -- the native thrower's use of it
   (wayne_b200/csrc/photons.cuh): splitmix64 hash of the exposure key, fixed Philox key,
-  counter (unit, hy + sub-sample, bin, hw ^ stream).
+  counter (e0, hy + sub-sample, bin, hw ^ stream) with e0 = 4 * unit = the index of the unit's
+  first electron in the bin's list (wide electrons first, each width padded to a multiple of 4).
 * ``thrower_fields`` -- the 16-bit radius / angle fields of a word and the uniforms they
   stand for (exact rationals; the device evaluates them in fp32 and then uses the SFU).
 """
@@ -40,9 +41,10 @@ def throw_keys(key0, key1):
     return z & MASK, z >> 32
 
 
-def thrower_words(unit, sample, bin_index, key, stream=STREAM_PHOTONS):
+def thrower_words(e0, sample, bin_index, key, stream=STREAM_PHOTONS):
+    """The four words of one unit (= four electrons); e0 = 4 * unit index within the bin."""
     hy, hw = throw_keys(*key)
-    return philox4x32_10([unit, (hy + sample) & MASK, bin_index, hw ^ stream], THROW_KEY)
+    return philox4x32_10([e0, (hy + sample) & MASK, bin_index, hw ^ stream], THROW_KEY)
 
 
 def thrower_fields(word):

@@ -177,13 +177,13 @@ def test_thrower_electrons_land_where_the_oracle_puts_them():
             wide = j < uh
             rem = (nh - 4 * j) if wide else (nl - 4 * (j - uh))
             sigma = float(np.float32(sigh[w] if wide else sigl[w]))
-            words = P.thrower_words(j, 0, w, key)
+            words = P.thrower_words(4 * j, 0, w, key)            # first counter word = the unit's first electron
             tail = None
             for h in range(min(4, rem)):
                 k, t = words[h] >> 16, words[h] & 0xffff
                 if k < 16:
                     if tail is None:
-                        tail = P.thrower_words(j, 0, w, key, P.STREAM_PHOTON_TAIL)
+                        tail = P.thrower_words(4 * j, 0, w, key, P.STREAM_PHOTON_TAIL)
                     u1 = (k + (tail[h] + 0.5) / 2.0 ** 32) / 65536.0
                 else:
                     u1 = (k + 0.5) / 65536.0

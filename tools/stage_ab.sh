@@ -3,7 +3,7 @@
 # usage: tools/stage_ab.sh "VAR=1" "OTHER=1 X=2" ...   (an empty string = defaults)
 for cfg in "$@"; do
   echo "== [$cfg]"
-  env $cfg python bench.py --steps 12 --warmup 4 --no-cpu 2>&1 | python -c "
+  env $cfg python bench.py --steps 12 --warmup 4 --no-cpu --no-extras 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

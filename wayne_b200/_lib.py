@@ -112,7 +112,7 @@ class ExposureArgs(C.Structure):
         ("add_flat", c_i32), ("add_sky", c_i32), ("add_gain", c_i32), ("add_dark", c_i32),
         ("add_nonlinear", c_i32), ("clip", c_i32), ("add_read_noise", c_i32), ("add_zero", c_i32),
         ("add_noise", c_i32), ("out_f32", c_i32),
-        ("key0", c_u32), ("key1", c_u32), ("pad0", c_i32),
+        ("key0", c_u32), ("key1", c_u32), ("device_inputs_ready", c_i32),
         ("scale", c_double), ("sky_rate", c_double), ("noise_mean", c_double), ("noise_std", c_double),
         ("depth_ld", c_i64),
         ("wl", c_void_p), ("flux", c_void_p), ("xref", c_void_p), ("yref", c_void_p), ("dur_ms", c_void_p),

@@ -75,7 +75,23 @@ struct wb200_ctx {
     };
     Buf planes[WB200_PLANE_COUNT];
     int64_t plane_count[WB200_PLANE_COUNT] = {};
-    Buf tables, trace, counts, totals, acc, cos_head, cos_next, tally;
+    Buf acc, tally;
+    // Two LANES of the per-exposure scratch that stage 1 and the count sampler write: the tables,
+    // traces and counts of exposure i+1 are made on the context's own `pre` stream while exposure
+    // i's electrons are still being thrown on the caller's stream (the thrower's grid drains over
+    // the duration of one CTA, the ramp pass runs at a third of the SM's warps: the count
+    // sampler's CTAs fill those holes).  `pre_done`: the lane's stage-1 work (recorded on `pre`);
+    // `freed`: the last kernel READING the lane has been queued on the caller's stream.
+    static constexpr int LANES = 2;
+    struct Lane {
+        Buf tables, trace, counts, totals, cos_head, cos_next;
+        cudaEvent_t pre_done = nullptr, freed = nullptr;
+        bool used = false;
+    } lane[LANES];
+    int next_lane = 0, last_lane = 0;
+    cudaStream_t pre = nullptr;
+    cudaEvent_t inputs = nullptr; // "device-resident inputs are ready" (recorded on the caller's stream)
+    bool overlap = true;          // WB200_CTX_SERIAL=1: everything on the caller's stream
 
     static constexpr int SLOTS = 6;
     struct Slot {
@@ -264,6 +280,17 @@ int wb200_ctx_create(int device, wb200_ctx **ctx_out)
         return wb::fail(WB200_ERR_NOMEM, "out of host memory%s%s");
     c->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&c->upload, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&c->pre, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaEventCreateWithFlags(&c->inputs, cudaEventDisableTiming);
+    for (int i = 0; i < wb200_ctx::LANES && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->lane[i].pre_done, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&c->lane[i].freed, cudaEventDisableTiming);
+    }
+    if (const char *env = getenv("WB200_CTX_SERIAL"))
+        c->overlap = atoi(env) == 0;
     for (int i = 0; i < wb200_ctx::SLOTS && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->slot[i].copied, cudaEventDisableTiming);
         if (e == cudaSuccess)
@@ -289,10 +316,22 @@ int wb200_ctx_destroy(wb200_ctx *c)
     for (auto &p : c->planes)
         if (p.d)
             cudaFree(p.d);
-    for (wb200_ctx::Buf *b : {&c->tables, &c->trace, &c->counts, &c->totals, &c->acc, &c->cos_head,
-                              &c->cos_next, &c->tally})
+    for (wb200_ctx::Buf *b : {&c->acc, &c->tally})
         if (b->d)
             cudaFree(b->d);
+    for (auto &l : c->lane) {
+        for (wb200_ctx::Buf *b : {&l.tables, &l.trace, &l.counts, &l.totals, &l.cos_head, &l.cos_next})
+            if (b->d)
+                cudaFree(b->d);
+        if (l.pre_done)
+            cudaEventDestroy(l.pre_done);
+        if (l.freed)
+            cudaEventDestroy(l.freed);
+    }
+    if (c->inputs)
+        cudaEventDestroy(c->inputs);
+    if (c->pre)
+        cudaStreamDestroy(c->pre);
     for (auto &m : c->marks) {
         cudaEventDestroy(m.a);
         cudaEventDestroy(m.b);
@@ -439,15 +478,18 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     const uint64_t launches0 = g_launches.load();
 
     // ---- scratch -------------------------------------------------------------------
-    CTX_STAGE(c, ctx_reserve(c, c->tables, sizeof(double) * 5 * W));
-    CTX_STAGE(c, ctx_reserve(c, c->trace, sizeof(double) * WB200_TRACE_STRIDE * N));
-    CTX_STAGE(c, ctx_reserve(c, c->counts, sizeof(int32_t) * (size_t)N * W));
-    CTX_STAGE(c, ctx_reserve(c, c->totals, sizeof(uint64_t) * N));
+    wb200_ctx::Lane &Ln = c->lane[c->next_lane];
+    c->last_lane = c->next_lane;
+    c->next_lane = (c->next_lane + 1) % wb200_ctx::LANES;
+    CTX_STAGE(c, ctx_reserve(c, Ln.tables, sizeof(double) * 5 * W));
+    CTX_STAGE(c, ctx_reserve(c, Ln.trace, sizeof(double) * WB200_TRACE_STRIDE * N));
+    CTX_STAGE(c, ctx_reserve(c, Ln.counts, sizeof(int32_t) * (size_t)N * W));
+    CTX_STAGE(c, ctx_reserve(c, Ln.totals, sizeof(uint64_t) * N));
     CTX_STAGE(c, ctx_reserve(c, c->tally, sizeof(uint64_t) * 4));
     CTX_STAGE(c, ctx_reserve(c, c->acc, sizeof(long long) * 15 * plane, /*zero=*/true));
     if (a->n_cosmics) {
-        CTX_STAGE(c, ctx_reserve(c, c->cos_head, sizeof(int32_t) * plane));
-        CTX_STAGE(c, ctx_reserve(c, c->cos_next, sizeof(int32_t) * a->n_cosmics));
+        CTX_STAGE(c, ctx_reserve(c, Ln.cos_head, sizeof(int32_t) * plane));
+        CTX_STAGE(c, ctx_reserve(c, Ln.cos_next, sizeof(int32_t) * a->n_cosmics));
     }
 
     // ---- stage the small inputs: ONE host->device copy on the upload stream ------------
@@ -522,22 +564,37 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     if (a->depth) // same stream, behind the small arrays: one FIFO, nothing overtakes anything
         CTX_CUDA(c, cudaMemcpyAsync(S.big, a->depth, big_bytes, cudaMemcpyHostToDevice, c->upload));
     CTX_CUDA(c, cudaEventRecord(S.copied, c->upload));
-    CTX_CUDA(c, cudaStreamWaitEvent(st, S.copied, 0));
+    // Stage 1 and the count sampler go on the context's `pre` stream (see wb200_ctx::Lane): ordered
+    // after the staging copy, after the last reader of this lane's buffers (the exposure before
+    // the previous one) and -- only when the caller hands over device-resident inputs it does not
+    // declare ready -- after what the caller's stream holds now.  With per-stage timing on, or
+    // WB200_CTX_SERIAL=1, everything stays on the caller's stream.
+    const bool side = c->overlap && !c->profile;
+    cudaStream_t ps = side ? c->pre : st;
+    if (side) {
+        if (Ln.used)
+            CTX_CUDA(c, cudaStreamWaitEvent(ps, Ln.freed, 0));
+        if ((a->d_flux || a->d_depth || a->d_cheb_coef) && !a->device_inputs_ready) {
+            CTX_CUDA(c, cudaEventRecord(c->inputs, st));
+            CTX_CUDA(c, cudaStreamWaitEvent(ps, c->inputs, 0));
+        }
+    }
+    CTX_CUDA(c, cudaStreamWaitEvent(ps, S.copied, 0));
     S.busy = true;
     auto dev = [&](size_t i) { return (void *)(S.d + pieces[i].off); };
     const double *d_wl = (const double *)dev(i_wl), *d_dur = (const double *)dev(i_dur);
     const double *d_flux = a->d_flux ? a->d_flux : (const double *)dev(i_flux);
 
     // ---- stage 1: tables and traces ---------------------------------------------------
-    double *tab = (double *)c->tables.d;
+    double *tab = (double *)Ln.tables.d;
     double *d_ratio = tab, *d_sigl = tab + W, *d_sigh = tab + 2 * W, *d_sens = tab + 3 * W, *d_dwl = tab + 4 * W;
-    mark_begin(c, 0, st);
+    mark_begin(c, 0, ps);
     CTX_STAGE(c, wb200_bin_tables(W, d_wl, I.psf_poly12, I.n_sens, (const double *)c->planes[WB200_PLANE_SENS_WL].d,
                                   (const double *)c->planes[WB200_PLANE_SENS_VAL].d, d_ratio, d_sigl, d_sigh,
-                                  d_sens, d_dwl, st));
+                                  d_sens, d_dwl, ps));
     CTX_STAGE(c, wb200_trace_table(N, (const double *)dev(i_x), (const double *)dev(i_y), I.trace_coeff9,
-                                   I.wl_sol9, (double *)c->trace.d, st));
-    mark_end(c, st);
+                                   I.wl_sol9, (double *)Ln.trace.d, ps));
+    mark_end(c, ps);
 
     // ---- counts -------------------------------------------------------------------------
     wb200_counts_args ca;
@@ -563,18 +620,23 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     ca.d_sens = d_sens;
     ca.d_dwl = d_dwl;
     ca.d_dur_ms = d_dur;
-    ca.d_counts = (int32_t *)c->counts.d;
-    ca.d_totals = (uint64_t *)c->totals.d;
-    mark_begin(c, 1, st);
-    CTX_STAGE(c, launch_counts(&ca, st));
-    mark_end(c, st);
+    ca.d_counts = (int32_t *)Ln.counts.d;
+    ca.d_totals = (uint64_t *)Ln.totals.d;
+    mark_begin(c, 1, ps);
+    CTX_STAGE(c, launch_counts(&ca, ps));
+    mark_end(c, ps);
 
     // ---- cosmic-ray chains (read by the per-pixel pass) ---------------------------------------
     if (a->n_cosmics) {
-        mark_begin(c, 2, st);
+        mark_begin(c, 2, ps);
         CTX_STAGE(c, wb200_cosmic_chains(a->n_cosmics, (const int32_t *)dev(i_cp), (int32_t)plane,
-                                         (int32_t *)c->cos_head.d, (int32_t *)c->cos_next.d, st));
-        mark_end(c, st);
+                                         (int32_t *)Ln.cos_head.d, (int32_t *)Ln.cos_next.d, ps));
+        mark_end(c, ps);
+    }
+
+    if (side) { // the caller's stream picks up when the lane's stage-1 work is complete
+        CTX_CUDA(c, cudaEventRecord(Ln.pre_done, ps));
+        CTX_CUDA(c, cudaStreamWaitEvent(st, Ln.pre_done, 0));
     }
 
     // ---- electrons: throw, bin, flat, accumulate ------------------------------------------
@@ -602,9 +664,9 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     pa.sub_scale = I.sub_scale;
     pa.key0 = a->key0;
     pa.key1 = a->key1;
-    pa.d_counts = (const int32_t *)c->counts.d;
-    pa.d_totals = (const uint64_t *)c->totals.d;
-    pa.d_trace = (const double *)c->trace.d;
+    pa.d_counts = (const int32_t *)Ln.counts.d;
+    pa.d_totals = (const uint64_t *)Ln.totals.d;
+    pa.d_trace = (const double *)Ln.trace.d;
     pa.d_wl = d_wl;
     pa.d_ratio = d_ratio;
     pa.d_sigl = d_sigl;
@@ -625,7 +687,7 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     ga.flat_wmin = I.flat_wmin;
     ga.flat_wmax = I.flat_wmax;
     ga.d_read_end = (const int32_t *)dev(i_re);
-    ga.d_trace = (const double *)c->trace.d;
+    ga.d_trace = (const double *)Ln.trace.d;
     for (int i = 0; i < 4; ++i)
         ga.d_flat[i] = (const double *)c->planes[WB200_PLANE_FLAT0 + i].d;
     ga.d_acc = (double *)c->acc.d;
@@ -674,8 +736,8 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
         for (int i = 0; i < 4; ++i)
             ra.d_nl[i] = c->planes[WB200_PLANE_NL0 + i].d;
     if (a->n_cosmics) {
-        ra.d_cos_head = (const int32_t *)c->cos_head.d;
-        ra.d_cos_next = (const int32_t *)c->cos_next.d;
+        ra.d_cos_head = (const int32_t *)Ln.cos_head.d;
+        ra.d_cos_next = (const int32_t *)Ln.cos_next.d;
         ra.d_cos_read = (const int32_t *)dev(i_cr);
         ra.d_cos_energy = (const double *)dev(i_ce);
     }
@@ -692,12 +754,14 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
         return rc;
     }
     if (a->d_stats) {
-        k_exposure_stats<<<1, 256, 0, st>>>(N, (const unsigned long long *)c->totals.d,
+        k_exposure_stats<<<1, 256, 0, st>>>(N, (const unsigned long long *)Ln.totals.d,
                                             (const unsigned long long *)c->tally.d, (unsigned long long *)a->d_stats);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CTX_CUDA(c, cudaGetLastError());
     }
     CTX_CUDA(c, cudaEventRecord(S.done, st));
+    CTX_CUDA(c, cudaEventRecord(Ln.freed, st));
+    Ln.used = true;
     c->exposures += 1;
     c->last_launches = (int64_t)(g_launches.load() - launches0);
     c->last_N = N;
@@ -755,7 +819,8 @@ int wb200_ctx_read_scratch(wb200_ctx *c, int which, void *host_out, int64_t byte
     WB_REQUIRE(c != nullptr, "null context");
     CTX_REQUIRE(c, host_out != nullptr && which >= 0 && which <= 3, "bad argument");
     const size_t N = (size_t)c->last_N, W = (size_t)c->last_W;
-    const wb200_ctx::Buf *b[4] = {&c->counts, &c->totals, &c->trace, &c->tables};
+    const wb200_ctx::Lane &Ll = c->lane[c->last_lane]; // the lane of the last exposure
+    const wb200_ctx::Buf *b[4] = {&Ll.counts, &Ll.totals, &Ll.trace, &Ll.tables};
     const size_t want[4] = {4 * N * W, 8 * N, 8 * WB200_TRACE_STRIDE * N, 8 * 5 * W};
     CTX_REQUIRE(c, b[which]->d && (size_t)bytes == want[which] && want[which] <= b[which]->cap,
                 "size does not match the last exposure");

@@ -98,6 +98,12 @@ struct PhotonParams {
     wb200_photon_args a;
     int sample0; // global index of the launch's first sub-sample (Philox counters)
     int n_split; // generic kernel: CTAs sharing one chunk's electrons (grid.z)
+    // native kernel: 1-D grid.  Blocks [0, fine_b0) take chunk_bins bins each, `chunks` per
+    // sub-sample; blocks from fine_b0 on belong to the LAST sub-samples (from fine_s0) and take
+    // fine_chunk bins each, fine_per per sub-sample, so that the grid drains in shorter quanta.
+    // (An experiment kept as an A/B switch, WB200_THROW_FINE: it measured slower, see throw_photons;
+    // by default fine_s0 = n_samples and every block is a full chunk.)
+    int chunks, fine_b0, fine_s0, fine_chunk, fine_per;
 };
 
 template <int TW, int TH>
@@ -122,7 +128,7 @@ __device__ __forceinline__ void to_window(const wb200_photon_args &a, int s_loca
 // round keys are instruction immediates (a run-time key costs ~9 constant loads per
 // call: ptxas re-loads kernel parameters inside the loop whatever the register
 // budget), over the counter
-//     (unit j of the bin, hy + sub-sample, bin, hw ^ WB_STREAM_PHOTONS)
+//     (4 j = first electron of unit j of the bin, hy + sub-sample, bin, hw ^ WB_STREAM_PHOTONS)
 // where (hy, hw) is a 64-bit hash of the exposure's (key0, key1) made on the host
 // (wb::throw_keys).  Philox is a bijection of the counter for any key, so distinct
 // (exposure, sub-sample, bin, unit) give distinct blocks; two exposures could only
@@ -178,12 +184,13 @@ __device__ __forceinline__ uint4 philox4x32_rounds2to10_fixed(uint4 c)
     return c;
 }
 
-// the whole call: counter (unit j, hy + sub-sample, bin, hw ^ stream)
-__device__ __forceinline__ uint4 philox4x32_10_throw(uint32_t j, uint32_t sample, uint32_t bin, ThrowKeys k,
+// the whole call: counter (e0, hy + sub-sample, bin, hw ^ stream), e0 = 4 * unit = the index of the
+// unit's first electron in the bin's list (wide electrons first, each width padded to a multiple of 4)
+__device__ __forceinline__ uint4 philox4x32_10_throw(uint32_t e0, uint32_t sample, uint32_t bin, ThrowKeys k,
                                                      uint32_t stream = WB_STREAM_PHOTONS)
 {
     uint32_t lo0, hi0, lo1, hi1;
-    mul_wide(j, WB_PHILOX_M0, lo0, hi0);
+    mul_wide(e0, WB_PHILOX_M0, lo0, hi0);
     mul_wide(bin, WB_PHILOX_M1, lo1, hi1);
     return philox4x32_rounds2to10_fixed(make_uint4((hi1 ^ (k.hy + sample)) ^ WB_TK0, lo1,
                                                    (hi0 ^ (k.hw ^ stream)) ^ WB_TK1, lo0));
@@ -437,13 +444,13 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
                     continue;
                 const int j = q - uex;
                 const ThrowKeys tk = throw_keys(a.key0, a.key1);
-                const uint4 r = philox4x32_10_throw((uint32_t)j, (uint32_t)s_glob, (uint32_t)(wb + b), tk);
+                const uint4 r = philox4x32_10_throw((uint32_t)(4 * j), (uint32_t)s_glob, (uint32_t)(wb + b), tk);
                 const bool wide = j < uuh;
                 const float sg = wide ? ush : usl;
                 const int rem = wide ? (unh - 4 * j) : (ucnt - unh - 4 * (j - uuh)); // electrons left
                 uint4 t = make_uint4(0, 0, 0, 0);
                 if (min(min(r.x, r.y), min(r.z, r.w)) < WB_TAIL_WORD)
-                    t = philox4x32_10_throw((uint32_t)j, (uint32_t)s_glob, (uint32_t)(wb + b), tk,
+                    t = philox4x32_10_throw((uint32_t)(4 * j), (uint32_t)s_glob, (uint32_t)(wb + b), tk,
                                             WB_STREAM_PHOTON_TAIL);
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(256) k_throw(const PhotonParams p)
 //     PRMT field extraction (no I2F), floor by the round-down magic-number add
 //     (FADD.RM, no F2I on the XU pipe);
 //   * tile-relative unsigned bounds tests and branch-free shared increments.
-// Same counters as the generic kernel's PHILOX path -- (unit, sub-sample, bin,
+// Same counters as the generic kernel's PHILOX path -- (first electron of the unit, sub-sample, bin,
 // stream) -- so a given key throws the same electrons whatever the launch geometry.
 // ---------------------------------------------------------------------------
 // keeps a CTA-uniform value in a vector register instead of letting ptxas rebuild it
@@ -661,6 +668,19 @@ __device__ __forceinline__ uint32_t select_in_box(float px, float hx, float py, 
     return r;
 }
 
+// the same with a third chained compare: `cell` only if also a > b (the electron exists)
+__device__ __forceinline__ uint32_t select_in_box_if_gt(float px, float hx, float py, float hy, int a, int b,
+                                                        uint32_t cell, uint32_t other)
+{
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 ax, ay;\n\tabs.ftz.f32 ax, %1;\n\tabs.ftz.f32 ay, %3;\n\t"
+        "setp.lt.ftz.f32 p, ax, %2;\n\tsetp.lt.and.ftz.f32 p, ay, %4, p;\n\tsetp.gt.and.s32 p, %7, %8, p;\n\t"
+        "selp.b32 %0, %5, %6, p;\n\t}"
+        : "=r"(r)
+        : "f"(px), "f"(hx), "f"(py), "f"(hy), "r"(cell), "r"(other), "r"(a), "r"(b));
+    return r;
+}
+
 // CTA-uniform values of the native thrower that only the rare paths read: shared memory
 struct ThrowShared {
     DirectSample ds;
@@ -675,7 +695,8 @@ struct ThrowShared {
 // The electrons of one lane's run of units.
 //   REPLAY = false  the hot loop: every electron of every unit is positioned; one inside the
 //                   accepted part of the tile (fast float test) increments its cell, one outside it
-//                   the warp's spare word `dump`, one that does not exist the word after it.
+//                   the warp's spare word `dump`, and so does one that does not exist (the warp
+//                   knows how many of those its group holds).
 //                   No branch depends on where an electron went.
 //   REPLAY = true   run again by a warp that found its spare word non-zero (an electron in ~4e6
 //                   leaves a tile that is clear of the frame's edges): the same units, the same
@@ -688,21 +709,34 @@ __device__ __forceinline__ void throw_run(const BinPar *pb, int j, int n, uint32
     constexpr int ROW_SHIFT = (TW == 64 ? 8 : TW == 128 ? 9 : TW == 256 ? 10 : 11);
     static_assert((4 * TW) == (1 << ROW_SHIFT), "ROW_SHIFT = log2(4 TW)");
     const uint32_t bias = sh.bias; // (a value ptxas cannot see: it would make it the immediate again)
-    int units_cur = 0x7fffffff; // units of the bin pb points at (known after the first load)
+    // The walk counts ELECTRONS, not units: j4 = 4 * (unit index) is the index of the unit's first
+    // electron within its bin's padded list, and it is also the first counter word of the unit's
+    // Philox call -- "this unit is used up" is then j4 >= nlx, the electrons left are n - j4, and
+    // no shift, no ceil(nlx / 4) and no separate unit counter are formed per trip.
+    int j4 = 4 * j;
+    static_assert(sizeof(BinPar) == 32, "the walk steps by 32 bytes");
+    uint32_t pba = (uint32_t)__cvta_generic_to_shared(pb);
+    int nlx_cur = 0x7fffffff; // padded electron count of the bin pb points at (known after the first load)
     do {
         // step to the next staged bin when this one is used up, then (re)load the bin:
         // branch-free -- at four electrons per unit some lane steps on most trips
-        const bool adv = j >= units_cur;
-        pb += adv ? 1 : 0;
-        j = adv ? 0 : j;
-        const BinPar cur = *pb;
-        units_cur = (cur.nlx + 3) >> 2;
+        // (one compare and two predicated instructions; as C++ selects ptxas spent five on it)
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, %2;\n\t@p add.u32 %0, %0, 32;\n\t@p mov.b32 %1, 0;\n\t}"
+            : "+r"(pba), "+r"(j4)
+            : "r"(nlx_cur));
+        BinPar cur;
+        asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+            : "=r"(cur.r1x), "=r"(cur.r1y), "=r"(cur.nh), "=r"(cur.nlx)
+            : "r"(pba));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];"
+            : "=f"(cur.fx), "=f"(cur.fy), "=f"(cur.sl), "=f"(cur.sh)
+            : "r"(pba));
+        nlx_cur = cur.nlx;
         const uint32_t r1x = cur.r1x, r1y = cur.r1y;
         uint32_t pjl, pjh;
-        mul_wide((uint32_t)j, WB_PHILOX_M0, pjl, pjh);
+        mul_wide((uint32_t)j4, WB_PHILOX_M0, pjl, pjh);
         const uint4 r = philox4x32_rounds2to10_fixed(make_uint4(r1x, r1y, pjh ^ cwk, pjl));
         // the unit's width and how many of its four electrons exist
-        const int j4 = 4 * j;
         const bool wide = j4 < cur.nh;
         const float sg = wide ? cur.sh : cur.sl;
         const int rem = (wide ? cur.nh : cur.nlx) - j4;
@@ -731,10 +765,16 @@ __device__ __forceinline__ void throw_run(const BinPar *pb, int j, int n, uint32
             const uint32_t bx = __float_as_uint(__fadd_rd(px, 12582912.0f));
             const uint32_t by = __float_as_uint(__fadd_rd(py, 12582912.0f));
             if (!REPLAY) {
-                uint32_t ad = select_in_box(px, hxf, py, hyf, cellk + (bx << 2) + (by << ROW_SHIFT), dump);
-                if (h > 0)
-                    ad = (rem > h) ? ad : dump + 4;
-                WB_DEV_ASSERT(ad >= dump - (uint32_t)(8 * 8 + TW * TH * 4) && ad <= dump + 4 && (ad & 3) == 0);
+                // one select: the cell if the electron exists AND lies in the accepted box, else the
+                // warp's spare word.  Electrons that do not exist (the last unit of a width holds 1..4)
+                // are counted there too; the warp knows how many its group has (`expect`), so only a
+                // count ABOVE that means that some electron left the box.
+                // (a predicated increment was tried: ATOMS.POPC.INC cannot be predicated -- ptxas
+                // branches around it -- and an ATOMS.ADD of 0 / 1 loses the POPC form)
+                const uint32_t cell = cellk + (bx << 2) + (by << ROW_SHIFT);
+                const uint32_t ad = (h == 0) ? select_in_box(px, hxf, py, hyf, cell, dump)
+                                             : select_in_box_if_gt(px, hxf, py, hyf, rem, h, cell, dump);
+                WB_DEV_ASSERT(ad >= dump - (uint32_t)(8 * 8 + TW * TH * 4) && ad <= dump && (ad & 3) == 0);
                 red_shared_inc(ad);
             } else {
                 if ((h > 0 && rem <= h) || (fabsf(px) < hxf && fabsf(py) < hyf))
@@ -750,7 +790,7 @@ __device__ __forceinline__ void throw_run(const BinPar *pb, int j, int n, uint32
                     atomicAdd(&sh.tally[1], 1u); // dropped like the reference's (pyparallel_menu.c:93)
             }
         }
-        ++j;
+        j4 += 4;
     } while (--n > 0);
 }
 
@@ -775,11 +815,19 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     __shared__ ThrowShared sh;
     __shared__ double s_pos[4]; // x = wl * [0] + [1], y = x * [2] + [3] (frame coordinates of a bin)
 
-    const int s_local = blockIdx.y;
-    const uint32_t s_glob = (uint32_t)(p.sample0 + s_local);
     const int W = a.n_bins;
-    const int w0 = blockIdx.x * a.chunk_bins;
-    const int w1 = min(W, w0 + a.chunk_bins);
+    int s_local, w0, w1;
+    if ((int)blockIdx.x < p.fine_b0) {
+        s_local = (int)blockIdx.x / p.chunks;
+        w0 = ((int)blockIdx.x - s_local * p.chunks) * a.chunk_bins;
+        w1 = min(W, w0 + a.chunk_bins);
+    } else {
+        const int b = (int)blockIdx.x - p.fine_b0, ds = b / p.fine_per;
+        s_local = p.fine_s0 + ds;
+        w0 = (b - ds * p.fine_per) * p.fine_chunk;
+        w1 = min(W, w0 + p.fine_chunk);
+    }
+    const uint32_t s_glob = (uint32_t)(p.sample0 + s_local);
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
@@ -922,6 +970,7 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
     const uint32_t cwk = pin_reg((keys.hw ^ WB_STREAM_PHOTONS) ^ WB_TK1);
 
     const int ngroups = (w1 - w0 + 31) >> 5;
+    int expect = 0; // electrons this warp has thrown at its spare word because they do not exist
     for (;;) {
         int g = 0;
         if (lane == 0)
@@ -969,6 +1018,9 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         bp.nh = nh;
         bp.nlx = cnt - nh + ((nh + 3) & ~3);
         const int units = (bp.nlx + 3) >> 2; // ceil(nh/4) wide ones, then ceil(nl/4) narrow ones
+        // electrons of the group's padded lists that do not exist: they are thrown at the spare word
+        // (a running total: the spare word is only cleared when a group is replayed)
+        expect += (int)__reduce_add_sync(FULL, (unsigned)(((-nh) & 3) + ((-(cnt - nh)) & 3)));
         mul_wide((uint32_t)w, WB_PHILOX_M1, bp.r1y, bp.r1x);
         bp.r1x ^= cyk;
         const int incl = warp_incl_scan(units);
@@ -1000,10 +1052,11 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         if (q < qend)
             throw_run<TW, TH, DIRECT, false>(pb, q - excl_b, qend - q, cwk, cellk, dump, hxf, hyf, sh);
         __syncwarp();
-        if (mydump[0] != 0) { // some electron of the group left the accepted part of the tile
+        if (mydump[0] != expect) { // some electron of the group left the accepted part of the tile
             __syncwarp();
             if (lane == 0)
                 mydump[0] = 0;
+            expect = 0;
             if (q < qend)
                 throw_replay<TW, TH, DIRECT>(pb, q - excl_b, qend - q, cwk, hxf, hyf, sh);
             __syncwarp();

@@ -35,8 +35,8 @@ constexpr size_t RN_SMEM = sizeof(float) * SKY_T * 2 * RN_THREADS + sizeof(doubl
 // exact for |q| < 2^51: q + bits(1.5 * 2^52), then subtract 1.5 * 2^52
 __device__ __forceinline__ double ll2d_fast(long long q)
 {
-    const long long lim = 1LL << 51;
-    if (q < lim && q > -lim)
+    // |q| < 2^51 <=> the high word lies in [-2^19, 2^19): one add and one unsigned compare
+    if ((unsigned)((int)(q >> 32) + (1 << 19)) < (1u << 20))
         return __longlong_as_double(q + 0x4338000000000000LL) - 6755399441055744.0;
     return (double)q;
 }
@@ -210,6 +210,22 @@ __device__ __forceinline__ double2 ld_plane2(const void *base, size_t idx)
     return ld_stream2(reinterpret_cast<const double *>(base) + idx);
 }
 
+__device__ __forceinline__ float2 ld_plane2_f32(const void *base, size_t idx)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];"
+                 : "=f"(r.x), "=f"(r.y)
+                 : "l"(reinterpret_cast<const float *>(base) + idx));
+    return r;
+}
+
+// np.clip: a NaN stays a NaN (fmin / fmax would return the bound), one compare and one select per bound
+__device__ __forceinline__ double clip_np(double v, double lo, double hi)
+{
+    v = (v < lo) ? lo : v;
+    return (v > hi) ? hi : v;
+}
+
 template <bool OUT32, bool PLANES32>
 __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_reads_args a)
 {
@@ -260,8 +276,8 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
         zc[1] = z.y;
     }
     if (a.clip) {
-        zc[0] = fmin(fmax(zc[0], a.clip_lo), a.clip_hi);
-        zc[1] = fmin(fmax(zc[1], a.clip_lo), a.clip_hi);
+        zc[0] = clip_np(zc[0], a.clip_lo, a.clip_hi);
+        zc[1] = clip_np(zc[1], a.clip_lo, a.clip_hi);
     }
     if (!in0)
         zc[0] = 0.0;
@@ -287,6 +303,7 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
     // ---- software pipeline: loads of read r+1 are in flight during read r -------
     longlong2 nq = make_longlong2(0, 0);
     double2 nacc = make_double2(0., 0.), ndk = make_double2(0., 0.), nde = make_double2(0., 0.);
+    float2 ndk32 = make_float2(0.f, 0.f), nde32 = make_float2(0.f, 0.f); // PLANES32: promoted at use
     double ndt = 0.0;
     auto issue = [&](int r) {
         const size_t off = (size_t)r * plane + p;
@@ -298,8 +315,13 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
         } else
             nacc = ld_stream2(reinterpret_cast<const double *>(a.d_acc) + off);
         if (dark_on) {
-            ndk = ld_plane2<PLANES32>(a.d_dark, off);
-            nde = ld_plane2<PLANES32>(a.d_dark_err, off);
+            if (PLANES32) {
+                ndk32 = ld_plane2_f32(a.d_dark, off);
+                nde32 = ld_plane2_f32(a.d_dark_err, off);
+            } else {
+                ndk = ld_plane2<false>(a.d_dark, off);
+                nde = ld_plane2<false>(a.d_dark_err, off);
+            }
         }
     };
     issue(0);
@@ -320,7 +342,8 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
             acc[0] = nacc.x;
             acc[1] = nacc.y;
         }
-        const double2 dk = ndk, de = nde;
+        const double2 dk = PLANES32 ? make_double2((double)ndk32.x, (double)ndk32.y) : ndk;
+        const double2 de = PLANES32 ? make_double2((double)nde32.x, (double)nde32.y) : nde;
         const double dt = ndt;
         if (r + 1 < R)
             issue(r + 1);
@@ -397,8 +420,8 @@ __global__ void __launch_bounds__(RN_THREADS, 5) k_reads_native(const wb200_read
             }
         }
         if (a.clip) {
-            v[0] = fmin(fmax(v[0], a.clip_lo), a.clip_hi);
-            v[1] = fmin(fmax(v[1], a.clip_lo), a.clip_hi);
+            v[0] = clip_np(v[0], a.clip_lo, a.clip_hi);
+            v[1] = clip_np(v[1], a.clip_lo, a.clip_hi);
         }
         if (!in0)
             v[0] = 0.0; // reset_reference_pixels (exposure.py:122-131)

@@ -86,7 +86,27 @@ int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, cons
             return launch_throw<WB200_RNG_PHILOX>(p, st);
         const ThrowKeys keys = throw_keys(a->key0, a->key1);
         const int chunks = (a->n_bins + a->chunk_bins - 1) / a->chunk_bins;
-        dim3 grid(chunks, a->n_samples);
+        // Optionally the last ~1.25 waves' worth of sub-samples in chunks 1/fine_div as long (see
+        // PhotonParams).  OFF by default: measured on the configs[3] shape it LOSES (1.891 ms with
+        // fine_div = 4 against 1.868 ms with equal CTAs) -- the grid does not drain in lock step, so
+        // there is no idle last wave to recover, and short CTAs pay tile set-up and flush more often.
+        int fine_div = 1;
+        if (const char *env = getenv("WB200_THROW_FINE")) // A/B switch
+            fine_div = atoi(env);
+        p.chunks = chunks;
+        p.fine_s0 = a->n_samples;
+        p.fine_chunk = a->chunk_bins;
+        p.fine_per = chunks;
+        if (fine_div > 1 && a->chunk_bins / fine_div >= 32) {
+            const int slots = 148 * WB_THROW_MIN_BLOCKS;
+            int n_fine = (slots + slots / 4 + chunks - 1) / chunks;
+            n_fine = n_fine < a->n_samples / 4 ? n_fine : a->n_samples / 4;
+            p.fine_s0 = a->n_samples - n_fine;
+            p.fine_chunk = (a->chunk_bins / fine_div + 31) / 32 * 32;
+            p.fine_per = (a->n_bins + p.fine_chunk - 1) / p.fine_chunk;
+        }
+        p.fine_b0 = p.fine_s0 * chunks;
+        dim3 grid(p.fine_b0 + (a->n_samples - p.fine_s0) * p.fine_per);
         const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int) + 64; // + two spare words per warp
         if (direct) {
             k_throw_philox<TILE_W, TILE_H, true><<<grid, 256, smem, st>>>(p, keys, *direct);

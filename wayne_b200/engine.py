@@ -952,6 +952,7 @@ class ExposureContext(object):
         check(lib.wb200_ctx_create(engine.device.index, C.byref(self._h)), "wb200_ctx_create")
         self._have = set()
         self._dark_reads = 0
+        self._seen_inputs = {}
         self._set_instrument()
 
     def __del__(self):
@@ -1070,11 +1071,35 @@ class ExposureContext(object):
                     "wb200_ctx_read_scratch")
         return out
 
+    def _device_input_ready(self, t):
+        """True when the device tensor ``t`` is known to be complete, i.e. nothing still queued on
+        the current stream produces it.  The first time a tensor (same storage, same version
+        counter) is seen, an event is recorded on the current stream; once that event has
+        completed the tensor is ready for good.  Lets the library start the next exposure's
+        tables and counts on its own stream while the previous exposure is still running
+        (wb200_exposure_args.device_inputs_ready) -- a visit keeps its stellar flux and its
+        planet-signal coefficients resident and hands the same tensors to every exposure.  (A
+        tensor rewritten in place by something torch does not see -- a foreign kernel through
+        data_ptr() -- must be handed over as a new tensor object.)"""
+        # keyed by the tensor OBJECT (a weak reference keeps the entry honest): a new tensor that the
+        # allocator put at a recycled address is a different object and is not ready
+        seen = self._seen_inputs
+        ent = seen.get(id(t))
+        if ent is not None and ent[0]() is t and ent[1] == t._version and ent[2] == t.data_ptr():
+            return ent[3].query()
+        if len(seen) > 64:
+            seen.clear()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.e.device))
+        seen[id(t)] = (weakref.ref(t), t._version, t.data_ptr(), ev)
+        return False
+
     def run(self, wl_um, flux, depth, depth_col0, xr, yr, dur_ms, dt_s, read_end, scale, key, count_mode,
             add_flat, sky_rate, add_gain, add_dark, add_nonlinear, clip, add_read_noise, add_zero, noise,
             cosmics, out_f32):
         """Queue one exposure on the current stream; returns (reads tensor [R+1][F][F], ContextRun)."""
         e = self.e
+        dev_inputs = []    # device-resident inputs of this exposure (see _device_input_ready)
         W, N, R = len(wl_um), len(xr), len(read_end)
         a = _lib.ExposureArgs()
         a.n_samples, a.n_bins, a.n_reads, a.count_mode = N, W, R, count_mode
@@ -1104,6 +1129,7 @@ class ExposureContext(object):
         if isinstance(flux, torch.Tensor):
             keep.append(flux)
             a.d_flux = flux.data_ptr()
+            dev_inputs.append(flux)
         else:
             a.flux = host(flux, name='flux')
         slot = None
@@ -1116,7 +1142,11 @@ class ExposureContext(object):
                 a.cheb_x = host(depth.x[depth_col0:depth_col0 + W])
                 coef = depth.coef[:N]
                 if isinstance(coef, torch.Tensor):
-                    coef = coef.contiguous()
+                    if not coef.is_contiguous():
+                        coef = coef.contiguous()
+                        dev_inputs.append(None)        # made just now on the current stream: not ready
+                    else:
+                        dev_inputs.append(coef)
                     keep.append(coef)
                     a.d_cheb_coef = coef.data_ptr()
                 else:
@@ -1126,6 +1156,7 @@ class ExposureContext(object):
                     if depth.dtype != torch.float64:
                         raise ValueError("device planet_signal must be float64")
                     d_depth = e.to_dev(depth)
+                    dev_inputs.append(d_depth if d_depth is depth else None)
                 else:
                     depth = np.asarray(depth)
                     if depth.dtype != np.float64 or not depth.flags.c_contiguous:
@@ -1147,6 +1178,7 @@ class ExposureContext(object):
             a.cos_energy = host(cosmics[2], name='cos_energy')
         stats = e.empty((4,), torch.int64)
         a.d_stats = stats.data_ptr()
+        a.device_inputs_ready = int(all(t is not None and self._device_input_ready(t) for t in dev_inputs))
         out = e.empty((R + 1, self.F, self.F), torch.float32 if out_f32 else torch.float64)
         self.profile(e.profile)
         e.mark('exposure', True)
