@@ -526,6 +526,7 @@ def run_native(args, wk):
     from wayne_b200.engine import bind_to_gpu_numa_node
     numa_bound = bind_to_gpu_numa_node(local) if world > 1 else False
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries the JSON line only
         dist.init_process_group('nccl', device_id=dev)
     calibration_dir(wk)
     from wayne import units as u
@@ -718,6 +719,21 @@ def run_native(args, wk):
     gc.enable()
     h2d_sep = 8 * (N + W) + inp['flux'].nbytes + inp['wl'].nbytes + 3 * 8 * N
 
+    # ---- what THIS box can move: concurrent pinned copies of the same sizes on the same GPUs ----
+    # (tools/copy_ceiling.py; a property of the host -- PCIe, the VM's memory path -- that the e2e
+    # legs above cannot exceed however fast the kernels are; measured here, on this box, in this run,
+    # because it differs from box to box: profiles/r02_copy_ceiling.json holds one box's 1/2/4/8 sweep)
+    ceiling = None
+    if not os.environ.get('WB200_NO_CEILING'):
+        try:
+            from tools.copy_ceiling import measure as copy_ceiling_measure
+            ceiling = copy_ceiling_measure(dev, world, 0.6, d2h_bytes=d2h, h2d_bytes=depth_host.nbytes)
+            ceiling.update(n_gpus=world, seconds_per_mode=0.6, d2h_bytes=int(d2h), h2d_bytes=int(depth_host.nbytes),
+                           source='tools/copy_ceiling.measure, this run, this box, all ranks at once')
+        except Exception as exc:      # noqa: BLE001
+            ceiling = None
+            sys.stderr.write('copy ceiling not measured: %r\n' % (exc,))
+
     # ---- BASELINE configs[4]: the multi-visit batch, exposure-wise over the ranks -------------
     multi_visit = None
     if not args.no_extras:
@@ -805,7 +821,8 @@ def run_native(args, wk):
                                                         else 1965.0) * 1e6 / 4) / 1e9,
                   'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
     dominant = max(((k, v) for k, v in stages.items() if k.startswith('k_')), key=lambda kv: kv[1][0])[0]
-    ceiling = copy_ceiling_for(world)
+    if ceiling is None:
+        ceiling = copy_ceiling_for(world)      # a committed sweep of another box, as a fallback
     e2e_val = world * 1e3 / ms_e2e
 
     def frac_of(key, v):

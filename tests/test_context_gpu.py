@@ -170,3 +170,52 @@ def test_stated_limits_are_enforced_and_accounted_for(calb_dir):
         else:
             assert stats[0] > 1e6 and stats[1] == 0 and stats[2] == stats[0]
         assert np.all(np.array([r[0] for r in exp.reads]) == 0)
+
+
+def test_overlapped_exposures_equal_serial_ones(calb_dir):
+    """Consecutive exposures overlap on the device (the next exposure's tables and counts are made
+    on the context's own stream, into the other scratch lane, beside the current electron throw;
+    include/wayne_b200.h).  Eight different exposures queued back to back -- host planet signals,
+    a device-resident one handed over repeatedly, none -- must give, bit for bit, the frames of
+    the same exposures run one at a time with everything on the caller's stream."""
+    import torch
+    from wayne import units as u
+    from wayne_b200.engine import DeviceEngine
+    from wayne_b200.lightcurve import SeparableSignal
+    eng = DeviceEngine.get()
+    wl, flux, planet = harness.spectrum(level=3.0e-14)
+    n = len(np.asarray(u.value_in(_gen()._gen_scanning_sample_times(100 * u.ms)[1], u.ms)))
+    dense = np.tile(planet, (n, 1)) * np.linspace(0.1, 1.0, n)[:, None]
+    dense_dev = torch.from_numpy(dense).to(eng.device)
+    torch.cuda.synchronize()
+
+    def signal(i):
+        return (None, dense * (1 + 0.1 * i), dense_dev,
+                SeparableSignal(np.linspace(0.2, 1.0, n) * (1 + 0.05 * i), planet))[i % 4]
+
+    def queue(i):
+        eg = _gen()
+        exp = eg.scanning_frame(x_ref=404.5 + 0.3 * i, y_ref=457.4 - 0.2 * i, x_jitter=0.02, y_jitter=0.02,
+                                wl=wl * u.micron, stellar_flux=flux * (1 + 0.02 * i), planet_signal=signal(i),
+                                scan_speed=7.4325 * u.pixel / u.s, sample_rate=100 * u.ms, cosmic_rate=11.,
+                                sky_background=5.5 * u.count / u.s, scale_factor=1.0 - 1e-3 * i,
+                                rng_key=(1963, 100 + i))
+        return eg, exp
+
+    assert not eng.profile
+    handles = [queue(i) for i in range(8)]                         # all eight in flight, overlapped
+    overlapped = [(np.array([r[0] for r in exp.reads]), eg.photons) for eg, exp in handles]
+    serial = []
+    eng.profile = True                                             # per-stage timing keeps an exposure on one stream
+    try:
+        for i in range(8):
+            eg, exp = queue(i)
+            serial.append((np.array([r[0] for r in exp.reads]), eg.photons))
+            torch.cuda.synchronize()
+    finally:
+        eng.profile = False
+        eng.stage_times()
+    for i in range(8):
+        assert overlapped[i][1] == serial[i][1] > 1e6, i
+        assert np.array_equal(overlapped[i][0], serial[i][0]), i
+    assert not np.array_equal(overlapped[0][0], overlapped[4][0])
