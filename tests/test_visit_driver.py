@@ -105,6 +105,14 @@ def test_short_visit_on_gpu(tmp_path, calb_dir):
     assert last.shape == (266, 266) and np.isfinite(last).all()
     sig = (last - zero)[5:-5, 5:-5]
     assert sig.sum() > 1e6 and sig[100:, :].sum() > 20 * abs(sig[:40, :].sum())    # the scan is on the frame
+    # the file a GPU exposure was written to, read back by the strict parser written from the FITS
+    # standard (tests/fits_standard.py shares nothing with wayne_b200.fitsio): layout of the reference's
+    # writer (wayne/exposure.py:133-214) and the same pixels
+    from tests import fits_standard as FS
+    hdus = FS.read(os.path.join(outdir, '0003_raw.fits'))
+    assert [h['EXTNAME'] for h, _, _ in hdus[1:]] == ['SCI', 'ERR', 'DQ', 'SAMP', 'TIME'] * 5
+    assert hdus[1][0]['BITPIX'] == -64 and hdus[1][0]['SAMPNUM'] == 4 and hdus[21][0]['SAMPNUM'] == 0
+    assert np.array_equal(hdus[1][2], last) and np.array_equal(hdus[21][2], zero)
     # same visit, exposure-wise over two "ranks": identical frames (keys do not depend on the partition)
     from wayne_b200 import params
     with open(pfile) as fh:
@@ -160,3 +168,53 @@ def test_sharded_visit_with_stochastic_ssv_is_partition_independent(tmp_path, ca
     for n in (1, 2, 3, 4):
         assert np.array_equal(frames['one'][n], frames['two'][n]), n
     assert not np.array_equal(frames['one'][1][-1], frames['one'][2][-1])
+
+
+@pytest.mark.gpu
+def test_compat_visit_equals_the_oracle_exposure_by_exposure(tmp_path, calb_dir, monkeypatch):
+    """The batched visit driver against the ORACLE, not against itself: a three-exposure visit in the
+    reference's stream mode (rng='numpy': one sequential numpy stream across the visit,
+    run_visit.py:73-77) must give, exposure by exposure, the reads of the numpy restatement of
+    ExposureGenerator.scanning_frame fed what Observation._generate_exposure hands it
+    (wayne/observation.py:415-504): per-exposure x_ref / y_ref / sky from the lists plus the linear
+    shifts (:446-453), the visit-trend factor of that exposure (:455-458, trend recomputed by the
+    oracle's hook_and_long_term_ramp), the sample times of the mode, 1 - light curves as the planet
+    signal (:441-443), and ONE RandomState consumed in exposure order."""
+    from oracle import exposure_oracle as E
+    from tests import harness
+    from wayne_b200 import params
+    from wayne.exposure_generator import ExposureGenerator
+    monkeypatch.setattr(params, 'rng', params.rng)                    # build_observation sets it globally
+    pfile = _write_visit(tmp_path, n_exp=3)
+    with open(pfile) as fh:
+        cfg = yaml.safe_load(fh)
+    cfg['general']['rng'] = 'numpy'
+    cfg['observation'].update(x_shifts=0.3, y_shifts=-0.2)
+    obs = run_visit.build_observation(cfg, str(tmp_path))            # np.random.seed(1963)
+    got = obs.run_observation(write_fits=False)
+    assert sorted(got) == [1, 2, 3]
+
+    cal = harness.oracle_calibration()
+    rs = np.random.RandomState(1963)
+    eg = ExposureGenerator(obs.detector, obs.grism, obs.NSAMP, obs.SAMPSEQ, obs.SUBARRAY, None, rng='numpy')
+    read_times = np.asarray(u.value_in(eg.read_times, u.s), dtype=float)
+    _, mid, dur, ri = eg._gen_scanning_sample_times(obs.sample_rate)
+    jd = np.array([float(u.value_in(t, u.day)) for t in obs.exp_start_times])
+    a1, b1, b2, to = cfg['trends']['visit_trend_coeffs']
+    t0 = E.gen_orbit_start_times_per_exp(jd, obs.visit_plan['orbit_start_index'])
+    trend = E.hook_and_long_term_ramp(jd, t0, a1, b1, b2, to)
+    xs, ys, sky = (np.loadtxt(str(tmp_path / f)) for f in ('xref.txt', 'yref.txt', 'sky.txt'))
+    wl = np.asarray(u.value_in(obs.wl, u.micron), dtype=float)
+    flux = np.asarray(getattr(obs.stellar_flux, 'value', obs.stellar_flux), dtype=float)
+    for i in range(3):
+        t = (mid + obs.exp_start_times[i]).to(u.day)
+        depth = 1.0 - obs.generate_lightcurves(t)                     # [n_samples][n_wl], observation.py:441-443
+        o = E.scanning_frame(cal, 'G141', 256, read_times, wl, flux, depth, xs[i] + 0.3 * i, ys[i] - 0.2 * i,
+                             0.025, 1e-15, 7.4325e-3, 100.0, rs, ssv=(1.5, 1.1, 0), cosmic_rate=11.,
+                             sky_background=float(sky[i]), scale_factor=float(trend[i]), threads=2)
+        reads = got[i + 1].reads
+        assert len(reads) == len(o['reads']) == 5
+        for r in range(5):
+            err = np.abs(reads[r][0] - o['reads'][r]).max()
+            assert err <= 1e-9 * max(1.0, np.abs(o['reads'][r]).max()), (i, r, err)
+    assert np.abs(got[1].reads[-1][0] - got[3].reads[-1][0]).max() > 1.0   # the exposures do differ
