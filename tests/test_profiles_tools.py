@@ -9,9 +9,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'tools'))
 
 
-def test_launch_shares_from_committed_csv(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("csv_name,bench_name", [('r01_launches_c4_s3.csv', 'r01_bench_c4_s3.json'),
+                                                  ('r02_launches_final.csv', 'r02_bench_c4_final.json')])
+def test_launch_shares_from_committed_csv(tmp_path, csv_name, bench_name):
     import ncu_summary
-    src = os.path.join(ROOT, 'profiles', 'r01_launches_c4_s3.csv')
+    src = os.path.join(ROOT, 'profiles', csv_name)
     dst = tmp_path / 'shares.txt'
     ncu_summary.launches(src, str(dst))
     text = dst.read_text()
@@ -22,7 +27,7 @@ def test_launch_shares_from_committed_csv(tmp_path):
     assert shares['k_throw_philox'] > 70 and shares['k_reads_native'] < 15 and shares['k_counts_window'] < 15
     # and it agrees with the live CUDA-event stage times of the committed bench line
     import json
-    line = json.loads(open(os.path.join(ROOT, 'profiles', 'r01_bench_c4_s3.json')).read().strip().splitlines()[-1])
-    st = line['stage_ms']
-    live = 100.0 * st['k_throw'] / sum(st.values())
+    line = json.loads(open(os.path.join(ROOT, 'profiles', bench_name)).read().strip().splitlines()[-1])
+    st = {k: v for k, v in line['stage_ms'].items() if k.startswith('k_')}
+    live = 100.0 * st['k_throw'] / (st['k_throw'] + st['k_reads'] + st['k_counts'])
     assert abs(live - shares['k_throw_philox']) < 3.0
