@@ -85,6 +85,36 @@ __device__ __forceinline__ void count_window_build(float *tbl, CountWindow &t, f
     t.k0 = k0;
 }
 
+// Poisson(lam) for the SMALL remainder mean (a few per cent of the cell's mean: ~0..6) by inversion of
+// one uniform, like poisson_inversion_u, but with the first eight terms of the chop-down search
+// unrolled and predicated: a warp's walk runs at the pace of its slowest lane (~lam + 3 sigma
+// dependent trips of ~10 instructions, 23 % of this kernel's instructions on the configs[3]
+// shape); straight-line, the eight steps are five instructions each with the reciprocals as
+// immediates, and only a lane beyond k = 8 (2e-3 of the draws at lam = 2.7) enters the loop.
+__device__ __forceinline__ int poisson_small_u(float u, float lam)
+{
+    u = fminf(u, 0.99999994f);
+    float p, s;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(-1.4426950408889634f * lam)); // e^-lam (lam < ~90)
+    s = p;
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j <= 8; ++j) {
+        k += (u > s) ? 1 : 0; // s = P(X <= j - 1)
+        p *= lam * (1.0f / (float)j);
+        s += p;
+    }
+    if (u > s) { // beyond k = 8: the rest of the search as in poisson_inversion_u
+        k = 8;
+        do {
+            ++k;
+            p *= lam * rcp_ftz((float)k);
+            s += p;
+        } while (u > s && !(p < 1e-10f && (float)k > lam));
+    }
+    return k;
+}
+
 __device__ __forceinline__ int count_window_draw(const float *tbl, const CountWindow &t, float u)
 {
     u = fminf(u, 0.99999994f);
@@ -210,7 +240,7 @@ k_counts_window(int N, int W, const double *__restrict__ flux, const double *__r
                 }
                 c = count_window_draw(tbl, win, u01f(wu));
                 if (rest > 0.0f)
-                    c += poisson_inversion_u(u01f(wu2), rest);
+                    c += poisson_small_u(u01f(wu2), rest);
             } else {
                 PhiloxStream g(k0, k1, (uint32_t)w, (uint32_t)s, WB_STREAM_COUNTS);
                 c = poisson_draw_fast(g, e);
