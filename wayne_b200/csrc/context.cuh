@@ -35,7 +35,7 @@ namespace wb {
 int launch_reads(const wb200_reads_args *a, cudaStream_t st);   // wayne_b200.cu
 int launch_counts(const wb200_counts_args *a, cudaStream_t st); // wayne_b200.cu
 int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct,
-                  int n_split);
+                  int n_split, const int *d_chunk_span);
 
 // electrons thrown / binned / dropped of one exposure, for the caller's bookkeeping
 __global__ void __launch_bounds__(256)
@@ -84,7 +84,7 @@ struct wb200_ctx {
     // `freed`: the last kernel READING the lane has been queued on the caller's stream.
     static constexpr int LANES = 2;
     struct Lane {
-        Buf tables, trace, counts, totals, cos_head, cos_next;
+        Buf tables, trace, counts, totals, cos_head, cos_next, span;
         cudaEvent_t pre_done = nullptr, freed = nullptr;
         bool used = false;
     } lane[LANES];
@@ -320,7 +320,7 @@ int wb200_ctx_destroy(wb200_ctx *c)
         if (b->d)
             cudaFree(b->d);
     for (auto &l : c->lane) {
-        for (wb200_ctx::Buf *b : {&l.tables, &l.trace, &l.counts, &l.totals, &l.cos_head, &l.cos_next})
+        for (wb200_ctx::Buf *b : {&l.tables, &l.trace, &l.counts, &l.totals, &l.cos_head, &l.cos_next, &l.span})
             if (b->d)
                 cudaFree(b->d);
         if (l.pre_done)
@@ -585,6 +585,23 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     const double *d_wl = (const double *)dev(i_wl), *d_dur = (const double *)dev(i_dur);
     const double *d_flux = a->d_flux ? a->d_flux : (const double *)dev(i_flux);
 
+    // ---- bins per CTA of the thrower (cached per set-up) ------------------------------------
+    if (c->chunk_bins == 0 || c->chunk_W != W || c->chunk_N != N || c->chunk_wl0 != a->wl[0] ||
+        c->chunk_wl1 != a->wl[W - 1]) {
+        c->chunk_bins = choose_chunk_bins(I, *a);
+        if (const char *env = getenv("WB200_CHUNK_BINS")) { // A/B switch (a multiple of 32)
+            const int v = atoi(env) / 32 * 32;
+            if (v >= 32)
+                c->chunk_bins = v;
+        }
+        c->chunk_W = W;
+        c->chunk_N = N;
+        c->chunk_wl0 = a->wl[0];
+        c->chunk_wl1 = a->wl[W - 1];
+    }
+    const int n_chunks = (W + c->chunk_bins - 1) / c->chunk_bins;
+    CTX_STAGE(c, ctx_reserve(c, Ln.span, sizeof(int) * 2 * (size_t)n_chunks));
+
     // ---- stage 1: tables and traces ---------------------------------------------------
     double *tab = (double *)Ln.tables.d;
     double *d_ratio = tab, *d_sigl = tab + W, *d_sigh = tab + 2 * W, *d_sens = tab + 3 * W, *d_dwl = tab + 4 * W;
@@ -592,6 +609,10 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     CTX_STAGE(c, wb200_bin_tables(W, d_wl, I.psf_poly12, I.n_sens, (const double *)c->planes[WB200_PLANE_SENS_WL].d,
                                   (const double *)c->planes[WB200_PLANE_SENS_VAL].d, d_ratio, d_sigl, d_sigh,
                                   d_sens, d_dwl, ps));
+    // first / last populated bin of every chunk: the thrower places its tiles from them
+    k_chunk_spans<<<n_chunks, 256, 0, ps>>>(W, c->chunk_bins, d_wl, d_flux, d_sens, d_dwl, (int *)Ln.span.d);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CTX_CUDA(c, cudaGetLastError());
     CTX_STAGE(c, wb200_trace_table(N, (const double *)dev(i_x), (const double *)dev(i_y), I.trace_coeff9,
                                    I.wl_sol9, (double *)Ln.trace.d, ps));
     mark_end(c, ps);
@@ -640,19 +661,6 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
     }
 
     // ---- electrons: throw, bin, flat, accumulate ------------------------------------------
-    if (c->chunk_bins == 0 || c->chunk_W != W || c->chunk_N != N || c->chunk_wl0 != a->wl[0] ||
-        c->chunk_wl1 != a->wl[W - 1]) {
-        c->chunk_bins = choose_chunk_bins(I, *a);
-        if (const char *env = getenv("WB200_CHUNK_BINS")) { // A/B switch (a multiple of 32)
-            const int v = atoi(env) / 32 * 32;
-            if (v >= 32)
-                c->chunk_bins = v;
-        }
-        c->chunk_W = W;
-        c->chunk_N = N;
-        c->chunk_wl0 = a->wl[0];
-        c->chunk_wl1 = a->wl[W - 1];
-    }
     CTX_CUDA(c, cudaMemsetAsync(c->tally.d, 0, sizeof(uint64_t) * 4, st));
     wb200_photon_args pa;
     memset(&pa, 0, sizeof(pa));
@@ -692,7 +700,7 @@ int wb200_exposure_run(wb200_ctx *c, const wb200_exposure_args *a, void *d_out, 
         ga.d_flat[i] = (const double *)c->planes[WB200_PLANE_FLAT0 + i].d;
     ga.d_acc = (double *)c->acc.d;
     mark_begin(c, 3, st);
-    CTX_STAGE(c, throw_photons(&pa, 0, st, &ga, 1));
+    CTX_STAGE(c, throw_photons(&pa, 0, st, &ga, 1, getenv("WB200_THROW_SCAN") ? nullptr : (const int *)Ln.span.d));
     mark_end(c, st);
 
     // ---- the per-pixel ramp pass ---------------------------------------------------------------

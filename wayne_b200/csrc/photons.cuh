@@ -104,6 +104,9 @@ struct PhotonParams {
     // (An experiment kept as an A/B switch, WB200_THROW_FINE: it measured slower, see throw_photons;
     // by default fine_s0 = n_samples and every block is a full chunk.)
     int chunks, fine_b0, fine_s0, fine_chunk, fine_per;
+    // native kernel, optional: [chunks][2] first / last bin of each full chunk that can hold
+    // electrons (k_chunk_spans; lo = -1: scan the chunk instead)
+    const int *d_chunk_span;
 };
 
 template <int TW, int TH>
@@ -849,7 +852,6 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         s_pos[2] = tc.m_t;
         s_pos[3] = tc.m_t * (a.sub_scale - tc.x_ref) + tc.c_t + tc.y_ref - a.sub_scale;
     }
-    __syncthreads();
     const size_t row = (size_t)s_local * W;
     auto bin_xy = [&](int w, double &x, double &y) {
         if (a.d_xpos) {
@@ -861,78 +863,102 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
         }
     };
 
-    // ---- place the tile on the chunk's footprint (as in the generic kernel) ----
-    float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
-    for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
-        if (a.d_counts[row + w] <= 0)
-            continue;
-        double x, y;
-        bin_xy(w, x, y);
-        if (!(fabs(x) < 1e9) || !(fabs(y) < 1e9))
-            continue;
-        xmin = fminf(xmin, (float)x);
-        xmax = fmaxf(xmax, (float)x);
-        ymin = fminf(ymin, (float)y);
-        ymax = fmaxf(ymax, (float)y);
+    // ---- place the tile on the chunk's footprint ----------------------------------------
+    // Bin positions are linear in the wavelength, so on a monotonic grid the footprint is spanned
+    // by the chunk's first and last populated bins, which stage 1 has found once per exposure
+    // (k_chunk_spans): one thread places the tile from those two positions while the others zero
+    // it.  Otherwise (explicit positions, a non-monotonic grid, the fine-grained tail) the chunk's
+    // counts and positions are scanned as in the generic kernel.
+    int span_lo = -1, span_hi = -1;
+    if (p.d_chunk_span && !a.d_xpos && (int)blockIdx.x < p.fine_b0) {
+        const int c = (int)blockIdx.x - s_local * p.chunks;
+        span_lo = p.d_chunk_span[2 * c];
+        span_hi = p.d_chunk_span[2 * c + 1];
     }
-    xmin = warp_min(xmin);
-    xmax = warp_max(xmax);
-    ymin = warp_min(ymin);
-    ymax = warp_max(ymax);
-    if (lane == 0) {
-        s_red[0][warp] = xmin;
-        s_red[1][warp] = xmax;
-        s_red[2][warp] = ymin;
-        s_red[3][warp] = ymax;
-    }
-    for (int i = threadIdx.x; i < TW * TH + 16; i += blockDim.x)
-        tile[i] = 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < nwarps; ++i) {
-            xmin = fminf(xmin, s_red[0][i]);
-            xmax = fmaxf(xmax, s_red[1][i]);
-            ymin = fminf(ymin, s_red[2][i]);
-            ymax = fmaxf(ymax, s_red[3][i]);
+    if (span_lo >= 0) {
+        // (thread 0 reads back the position constants it has just written itself: no barrier yet)
+        if (threadIdx.x == 0) {
+            double x0, y0, x1, y1;
+            bin_xy(span_lo, x0, y0);
+            bin_xy(span_hi, x1, y1);
+            int ox = 0, oy = 0;
+            if (fabs(x0) < 1e9 && fabs(y0) < 1e9 && fabs(x1) < 1e9 && fabs(y1) < 1e9) {
+                ox = (int)floorf(0.5f * ((float)x0 + (float)x1)) - TW / 2;
+                oy = (int)floorf(0.5f * ((float)y0 + (float)y1)) - TH / 2;
+            }
+            s_org[0] = ox;
+            s_org[1] = oy;
         }
-        int ox = 0, oy = 0;
-        if (xmin <= xmax) {
-            ox = (int)floorf(0.5f * (xmin + xmax)) - TW / 2;
-            oy = (int)floorf(0.5f * (ymin + ymax)) - TH / 2;
+        for (int i = threadIdx.x; i < TW * TH + 16; i += blockDim.x)
+            tile[i] = 0;
+    } else {
+        __syncthreads(); // the position constants
+        float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+        for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+            if (a.d_counts[row + w] <= 0)
+                continue;
+            double x, y;
+            bin_xy(w, x, y);
+            if (!(fabs(x) < 1e9) || !(fabs(y) < 1e9))
+                continue;
+            xmin = fminf(xmin, (float)x);
+            xmax = fmaxf(xmax, (float)x);
+            ymin = fminf(ymin, (float)y);
+            ymax = fmaxf(ymax, (float)y);
         }
-        s_org[0] = ox;
-        s_org[1] = oy;
+        xmin = warp_min(xmin);
+        xmax = warp_max(xmax);
+        ymin = warp_min(ymin);
+        ymax = warp_max(ymax);
+        if (lane == 0) {
+            s_red[0][warp] = xmin;
+            s_red[1][warp] = xmax;
+            s_red[2][warp] = ymin;
+            s_red[3][warp] = ymax;
+        }
+        for (int i = threadIdx.x; i < TW * TH + 16; i += blockDim.x)
+            tile[i] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < nwarps; ++i) {
+                xmin = fminf(xmin, s_red[0][i]);
+                xmax = fmaxf(xmax, s_red[1][i]);
+                ymin = fminf(ymin, s_red[2][i]);
+                ymax = fmaxf(ymax, s_red[3][i]);
+            }
+            int ox = 0, oy = 0;
+            if (xmin <= xmax) {
+                ox = (int)floorf(0.5f * (xmin + xmax)) - TW / 2;
+                oy = (int)floorf(0.5f * (ymin + ymax)) - TH / 2;
+            }
+            s_org[0] = ox;
+            s_org[1] = oy;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int tx0 = s_org[0], ty0 = s_org[1];
-    // accepted tile-relative range [lo, lo+n): frame test 0 < x < nr, 0 < y < nc ...
-    const int lox = max(0, 1 - tx0), loy = max(0, 1 - ty0);
-    // ... trimmed to an even size and CENTRED: with hx = n/2 the fast test of an electron at
-    // centred coordinate p is |p| < hx -- one float compare per axis on the coordinate itself --
-    // and everything that fails it (the trimmed last column included) takes the exact slow path
-    const int hx = max(0, min(TW, a.nr - tx0) - lox) >> 1, hy = max(0, min(TH, a.nc - ty0) - loy) >> 1;
-    // Bin positions are staged relative to the CENTRE of the accepted range, frame pixel
-    // (ax0, ay0).  floor() of a centred coordinate p comes from the round-down magic add:
-    // bits(p + 1.5 2^23) = 0x4B400000 + floor(p), and the tile cell of (floor px, floor py) is
-    //     tile + ((fy + loy + hy) TW + fx + lox + hx) 4  =  cellk + (bits_x << 2) + (bits_y << log2(4 TW))
-    // with every constant (the two magic offsets too: shifts and adds wrap mod 2^32) folded into
-    // cellk -- no subtraction, no separate address arithmetic per electron.
-    static_assert((TW & (TW - 1)) == 0, "TW must be a power of two");
-    constexpr int ROW_SHIFT = (TW == 64 ? 8 : TW == 128 ? 9 : TW == 256 ? 10 : 11);
-    const int ax0 = tx0 + lox + hx, ay0 = ty0 + loy + hy;
-    const float hxf = (float)hx, hyf = (float)hy;
-    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-    const uint32_t cellk = pin_reg(tile_s + (uint32_t)(((loy + hy) * TW + lox + hx) * 4) - (0x4B400000u << 2) -
-                                   (0x4B400000u << ROW_SHIFT));
-    const uint32_t dump = pin_reg(tile_s + (uint32_t)(TW * TH * 4 + warp * 8));
-    int *const mydump = tile + TW * TH + warp * 2;
-    // the sub-sample's flat-field / accumulation constants are CTA-uniform and only used by
-    // the flush and by electrons that leave the tile: shared memory, not registers
+    // accepted tile-relative range [lo, lo+n): frame test 0 < x < nr, 0 < y < nc, trimmed to an even
+    // size and CENTRED: with hx = n/2 the fast test of an electron at centred coordinate p is
+    // |p| < hx -- one float compare per axis on the coordinate itself -- and everything that fails
+    // it (the trimmed last column included) takes the exact slow path
+    auto accepted = [&](int tx0, int ty0, int &lox, int &loy, int &hx, int &hy) {
+        lox = max(0, 1 - tx0);
+        loy = max(0, 1 - ty0);
+        hx = max(0, min(TW, a.nr - tx0) - lox) >> 1;
+        hy = max(0, min(TH, a.nc - ty0) - loy) >> 1;
+    };
+    // the sub-sample's flat-field / accumulation constants are CTA-uniform and only used by the flush
+    // and by electrons that leave the tile: shared memory, not registers.  Thread 0 fills them in
+    // right behind the tile origin (which it wrote itself), so that ONE barrier publishes the
+    // position constants, the origin, these and the zeroed tile.
+    __shared__ int s_next; // next 32-bin group to hand out (dynamic: counts are ragged)
     if (threadIdx.x == 0) {
+        int lox, loy, hx, hy;
+        accepted(s_org[0], s_org[1], lox, loy, hx, hy);
+        s_next = 0;
         sh.hx = hx;
         sh.hy = hy;
-        sh.ax0 = ax0;
-        sh.ay0 = ay0;
+        sh.ax0 = s_org[0] + lox + hx;
+        sh.ay0 = s_org[1] + loy + hy;
         sh.wox = sh.woy = 0;
         sh.s_local = s_local;
         sh.tally[0] = sh.tally[1] = 0u;
@@ -959,10 +985,25 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             ds.acc = reinterpret_cast<long long *>(ga.d_acc) + (size_t)r * ga.F * ga.F;
         }
     }
-    __shared__ int s_next; // next 32-bin group to hand out (dynamic: counts are ragged)
-    if (threadIdx.x == 0)
-        s_next = 0;
     __syncthreads();
+    const int tx0 = s_org[0], ty0 = s_org[1];
+    int lox, loy, hx, hy;
+    accepted(tx0, ty0, lox, loy, hx, hy);
+    // Bin positions are staged relative to the CENTRE of the accepted range, frame pixel
+    // (ax0, ay0).  floor() of a centred coordinate p comes from the round-down magic add:
+    // bits(p + 1.5 2^23) = 0x4B400000 + floor(p), and the tile cell of (floor px, floor py) is
+    //     tile + ((fy + loy + hy) TW + fx + lox + hx) 4  =  cellk + (bits_x << 2) + (bits_y << log2(4 TW))
+    // with every constant (the two magic offsets too: shifts and adds wrap mod 2^32) folded into
+    // cellk -- no subtraction, no separate address arithmetic per electron.
+    static_assert((TW & (TW - 1)) == 0, "TW must be a power of two");
+    constexpr int ROW_SHIFT = (TW == 64 ? 8 : TW == 128 ? 9 : TW == 256 ? 10 : 11);
+    const int ax0 = tx0 + lox + hx, ay0 = ty0 + loy + hy;
+    const float hxf = (float)hx, hyf = (float)hy;
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t cellk = pin_reg(tile_s + (uint32_t)(((loy + hy) * TW + lox + hx) * 4) - (0x4B400000u << 2) -
+                                   (0x4B400000u << ROW_SHIFT));
+    const uint32_t dump = pin_reg(tile_s + (uint32_t)(TW * TH * 4 + warp * 8));
+    int *const mydump = tile + TW * TH + warp * 2;
     const int wox = sh.wox, woy = sh.woy;
     BinPar *mybins = s_bin[warp];
     // round-1 constants of the thrower's Philox stream (see ThrowKeys)

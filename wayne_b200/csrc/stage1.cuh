@@ -79,6 +79,57 @@ __global__ void k_bin_tables(int W, const double *__restrict__ wl, const Poly12 
     dwl[w] = g0 + g1;
 }
 
+// Per chunk of `chunk_bins` bins (one CTA of the native thrower): the first and the last bin that
+// can hold electrons at all (flux * sensitivity * width > 0), or lo = -1 when the wavelength grid is
+// not monotonic inside the chunk.  Bin positions are linear in the wavelength (wl_to_x, wl_to_y),
+// so on a monotonic grid the footprint of a chunk in ANY sub-sample is spanned by those two bins:
+// the thrower places its tile from them instead of scanning the chunk's counts and positions
+// (a 2048-bin pass and two barriers at the head of every CTA).  span[2c] = lo, span[2c+1] = hi.
+__global__ void k_chunk_spans(int W, int chunk_bins, const double *__restrict__ wl,
+                              const double *__restrict__ flux, const double *__restrict__ sens,
+                              const double *__restrict__ dwl, int *span)
+{
+    __shared__ int s_lo, s_hi, s_bad;
+    const int w0 = blockIdx.x * chunk_bins, w1 = min(W, w0 + chunk_bins);
+    if (threadIdx.x == 0) {
+        s_lo = 0x7fffffff;
+        s_hi = -1;
+        s_bad = 0;
+    }
+    __syncthreads();
+    int lo = 0x7fffffff, hi = -1, bad = 0;
+    for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+        const double e = flux[w] * sens[w] * dwl[w];
+        if (e > 0.0) { // (false for NaN)
+            lo = min(lo, w);
+            hi = max(hi, w);
+        }
+        const double a = wl[w];
+        if (!(fabs(a) < 1e300) || (w + 1 < w1 && !(wl[w + 1] >= a) && !(wl[w + 1] <= a)))
+            bad = 1; // NaN / inf
+    }
+    // monotonic either way: every step has the sign of the chunk's end-to-end difference
+    if (w1 - w0 > 1) {
+        const double d = wl[w1 - 1] - wl[w0];
+        for (int w = w0 + threadIdx.x; w + 1 < w1; w += blockDim.x) {
+            const double step = wl[w + 1] - wl[w];
+            if ((d >= 0 && step < 0) || (d <= 0 && step > 0))
+                bad = 1;
+        }
+    }
+    if (lo <= hi) {
+        atomicMin(&s_lo, lo);
+        atomicMax(&s_hi, hi);
+    }
+    if (bad)
+        atomicOr(&s_bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        span[2 * blockIdx.x] = s_bad ? -1 : (s_lo <= s_hi ? s_lo : w0);
+        span[2 * blockIdx.x + 1] = s_lo <= s_hi ? s_hi : w0;
+    }
+}
+
 struct TraceCoef {
     double x_ref, y_ref, m_t, c_t, m_w, c_w, m_wl, c_wl;
 };

@@ -63,7 +63,7 @@ static int launch_throw(const PhotonParams &p, cudaStream_t st)
 }
 
 int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, const wb200_gather_args *direct,
-                  int n_split = 1)
+                  int n_split = 1, const int *d_chunk_span = nullptr)
 {
     WB_REQUIRE(a != nullptr, "null args");
     WB_REQUIRE(a->n_samples >= 0 && a->n_bins > 0, "bad sizes");
@@ -79,6 +79,8 @@ int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, cons
     p.a = *a;
     p.sample0 = sample0;
     p.n_split = n_split;
+    p.chunks = p.fine_b0 = p.fine_s0 = p.fine_chunk = p.fine_per = 0;
+    p.d_chunk_span = nullptr;
     WB_REQUIRE(!direct || a->rng_mode == WB200_RNG_PHILOX, "direct accumulation is a native-mode path");
     switch (a->rng_mode) {
     case WB200_RNG_PHILOX: {
@@ -106,6 +108,7 @@ int throw_photons(const wb200_photon_args *a, int sample0, cudaStream_t st, cons
             p.fine_per = (a->n_bins + p.fine_chunk - 1) / p.fine_chunk;
         }
         p.fine_b0 = p.fine_s0 * chunks;
+        p.d_chunk_span = d_chunk_span;
         dim3 grid(p.fine_b0 + (a->n_samples - p.fine_s0) * p.fine_per);
         const size_t smem = (size_t)TILE_W * TILE_H * sizeof(int) + 64; // + two spare words per warp
         if (direct) {
