@@ -1021,6 +1021,8 @@ k_throw_philox(const PhotonParams p, const ThrowKeys keys, const wb200_gather_ar
             break;
         const int wb = w0 + (g << 5);
         const int w = wb + lane;
+        // (prefetching the counts of the group this warp is likely to take next into L1 was tried:
+        // 1.841 against 1.828 ms)
         BinPar bp;
         int cnt = 0, nh = 0;
         bp.fx = bp.fy = bp.sl = bp.sh = 0.f;
