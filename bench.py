@@ -8,7 +8,7 @@ A "step" is one full exposure (stages 1-4: trace/dispersion/sensitivity, Philox
 Poisson counts, electron throw + binning, flat-field gather, fused per-pixel
 ramp pass).  Workload at N=1 = BASELINE.json configs[3], the configuration the
 metric is quoted on: G141 spatial scan, 1024^2 full frame, NSAMP=15 RAPID,
-10 ms sub-samples (4110 of them), 4096 wavelength bins, ~1e9 photons.
+10 ms sub-samples (4116 of them), 4096 wavelength bins, ~1e9 photons.
 
   value   exposures/s with the exposure's inputs already resident in HBM and the
           reads left in HBM (CUDA events on the launching stream, max over ranks)
@@ -17,8 +17,14 @@ metric is quoted on: G141 spatial scan, 1024^2 full frame, NSAMP=15 RAPID,
           NSAMP reads inside the timed region (copies of consecutive exposures
           overlap the kernels: upload / compute / download streams; every
           exposure's reads are touched on the host before the clock stops)
-  roofline / roofline_hbm   per-kernel, durations from CUDA events recorded around
-          each launch inside the timed region
+  roofline / roofline_hbm   per-kernel, durations from CUDA events recorded around each
+          launch, one kernel at a time, over 4-12 exposures of the same inputs right AFTER the
+          timed region (per-stage events keep an exposure on one stream; inside the timed
+          region consecutive exposures may overlap) -- `stage_ms`
+  e2e.copy_ceiling / frac_of_copy_ceiling   what THIS box moves with concurrent pinned copies
+          of the same sizes on the same GPUs and nothing else running (tools/copy_ceiling.py,
+          0.6 s per mode, all ranks at once): the bound of every e2e figure, and the e2e
+          figure as a fraction of it
   cpu_baseline   the oracle (unmodified reference C kernel when it was compiled
           in the build container, else the C port) + numpy restatement, timed on
           this host on a bounded sample of the same exposure
