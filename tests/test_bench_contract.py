@@ -47,3 +47,17 @@ def test_native_arm_line():
     c = d['clocks']
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(c)
     assert {'value', 'unit', 'cores', 'kind', 'sample'} <= set(d['cpu_baseline'])
+
+
+def test_every_rank_gets_physical_inputs():
+    """Ranks key their exposures with rank * 100000 + i.  The per-exposure inputs derived from
+    that index must stay physical for every rank (a visit-trend factor that went negative for
+    ranks > 0 once made every multi-GPU run throw zero electrons and fail its own bookkeeping)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    wk = bench.WORKLOADS['c4']
+    for rank in (0, 1, 7):
+        for i in (0, 7, 63, 999):
+            kw = bench.frame_kwargs(wk, rank * 100000 + i)
+            assert 0.98 < kw['scale_factor'] <= 1.0, (rank, i, kw['scale_factor'])
+            assert abs(kw['x_ref'] - wk['x_ref']) < 0.5 and abs(kw['y_ref'] - wk['y_ref']) < 0.5
