@@ -219,3 +219,28 @@ def test_overlapped_exposures_equal_serial_ones(calb_dir):
         assert overlapped[i][1] == serial[i][1] > 1e6, i
         assert np.array_equal(overlapped[i][0], serial[i][0]), i
     assert not np.array_equal(overlapped[0][0], overlapped[4][0])
+
+
+def test_tile_placement_from_chunk_spans_equals_the_scan(calb_dir, monkeypatch):
+    """The native thrower places each CTA's tile from the chunk's first / last populated bins
+    (k_chunk_spans in stage 1) instead of scanning the chunk's counts and positions.  Where the
+    tile sits only decides which electrons take the slow path, never where they land: the frames
+    with WB200_THROW_SCAN=1 (the scan) must be bit-identical."""
+    from wayne import units as u
+    from wayne.trend_generators.scan_speed_varations import SSVSine
+    wl, flux, planet = harness.spectrum(level=3.0e-14)
+    flux = np.array(flux, dtype=float)
+    flux[: len(flux) // 3] = 0.0                 # a dark stretch: the span starts inside the first chunk
+    kw = dict(x_ref=404.5, y_ref=457.4, x_jitter=0.02, y_jitter=0.02, wl=wl * u.micron, stellar_flux=flux,
+              planet_signal=None, scan_speed=7.4325 * u.pixel / u.s, sample_rate=100 * u.ms,
+              ssv_generator=SSVSine(1.5, 1.1, 0), cosmic_rate=11., sky_background=5.5 * u.count / u.s,
+              rng_key=(1963, 77))
+    out = {}
+    for scan in (False, True):
+        if scan:
+            monkeypatch.setenv('WB200_THROW_SCAN', '1')
+        eg = _gen()
+        exp = eg.scanning_frame(**kw)
+        out[scan] = (np.array([r[0] for r in exp.reads]), eg.photons)
+    assert out[False][1] == out[True][1] > 1e5
+    assert np.array_equal(out[False][0], out[True][0])
