@@ -826,6 +826,9 @@ def run_native(args, wk):
                   'mufu_bound_gelectron_s': (148 * 16 * (clocks['sm_mhz'] if clocks and clocks.get('sm_mhz')
                                                         else 1965.0) * 1e6 / 4) / 1e9,
                   'traffic': traffic.get('k_throw'), 'traffic_source': traffic.get('source'), 'ms': t_throw}
+    # the same achieved rate against the hardware bound that does not depend on the recipe's own
+    # microbenchmark: four MUFU per electron at one warp-instruction per 8 cycles per sub-partition
+    roof_throw['frac_of_mufu_bound'] = roof_throw['achieved'] / roof_throw['mufu_bound_gelectron_s']
     dominant = max(((k, v) for k, v in stages.items() if k.startswith('k_')), key=lambda kv: kv[1][0])[0]
     if ceiling is None:
         ceiling = copy_ceiling_for(world)      # a committed sweep of another box, as a fallback
